@@ -1,0 +1,184 @@
+/*
+ * clipn.h — C ABI of libclipn.so: the B200 (sm_100a) CLIP train-step kernels.
+ *
+ * This is the drop-in boundary for the reference's hot path.  Every entry point replaces one
+ * (group of) ATen/cuBLAS/NCCL call(s) the reference makes; the citation on each function is
+ * `file:line` under /root/reference/src/open_clip.  INTEGRATION.md shows the ctypes binding a
+ * reference maintainer would add and where each call slots into model.py / loss.py.
+ *
+ * Conventions
+ *   - Plain C: raw device pointers, sizes, a CUDA stream handle.  No torch types.
+ *   - The CALLER owns all memory (outputs, workspaces); the library never allocates or frees
+ *     device memory and never synchronises the host with the device.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 on success, negative on error; clipn_last_error() returns a message
+ *     (thread-local).  No exceptions cross the ABI.
+ *   - Activations are bf16 row-major; statistics / reductions / master gradients are fp32.
+ *   - Re-entrant: no global mutable state besides a read-only device-property cache.
+ */
+#ifndef CLIPN_H_
+#define CLIPN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* clipn_stream_t; /* cudaStream_t */
+
+#define CLIPN_OK 0
+#define CLIPN_ERR_ARG (-1)
+#define CLIPN_ERR_CUDA (-2)
+
+/* ---- library ------------------------------------------------------------------------------ */
+int clipn_version(void);
+const char* clipn_last_error(void);
+/* sm count / compute capability of the current device */
+int clipn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- GEMM family (tcgen05 + TMEM + TMA) ----------------------------------------------------
+ * C[M,N] = epilogue( alpha * sum_k A(m,k) * B(n,k) )
+ *   A: a_mn_major == 0 -> stored [M,K] row-major (lda = row pitch in elements, K contiguous)
+ *      a_mn_major == 1 -> stored [K,M] row-major (M contiguous)           (weight-gradient form)
+ *   B: b_mn_major == 0 -> stored [N,K] row-major (torch Linear weight)    (F.linear form)
+ *      b_mn_major == 1 -> stored [K,N] row-major                          (x @ W form)
+ * Replaces: F.linear x3 on in_proj chunks transformer.py:195-197, out_proj :246, mlp c_fc/c_proj
+ * :295-299, conv1-as-GEMM :794, `pooled @ proj` :923, `x @ text_projection` model.py:409, and their
+ * autograd dgrad/wgrad (cuBLASLt in the reference).
+ */
+enum clipn_epilogue {
+  CLIPN_EPI_STORE = 0,      /* C(bf16) = alpha*acc (+ bias[n])                                         */
+  CLIPN_EPI_BIAS_GELU = 1,  /* t = bf16(acc + bias); C = t (pre-activation, saved for backward);
+                               C2 = bf16(gelu_erf(t))           (c_fc + nn.GELU, transformer.py:295-299) */
+  CLIPN_EPI_BIAS_RESID = 2, /* C = bf16( bf16(acc + bias) + aux[m,n] )   (out_proj/c_proj + residual
+                               add, transformer.py:328-329)                                               */
+  CLIPN_EPI_DGELU = 3,      /* h = aux[m,n]; C = bf16(acc * gelu'(h)); C2 = bf16(gelu(h))  (GELU bwd fused
+                               into the c_proj dgrad; C2 re-materialises the c_proj wgrad operand)        */
+  CLIPN_EPI_ACCUM_F32 = 4,  /* C(f32)[m,n] += alpha*acc   (split-K weight gradient, red.global.add)      */
+  CLIPN_EPI_STORE_F32 = 5,  /* C(f32) = alpha*acc (+ bias)                                               */
+  CLIPN_EPI_LSE = 6,        /* no C.  Online row log-sum-exp partials of alpha*acc (+logit_bias):
+                               part_max/part_sum[(n_tile*2+half)*M + m], and the label logit
+                               (column == m + label_offset) into pos[m]  (ClipLoss fwd, loss.py:102-139)   */
+  CLIPN_EPI_CLIP_DLOGITS = 7, /* C(bf16)[m,n] = gscale*( exp(s-row_lse[m]) + exp(s-col_lse[n])*col_w
+                               - (1+col_w)*[n == m+label_offset] ), s = alpha*acc (+logit_bias);
+                               also accumulates d(loss)/d(logit_scale) (ClipLoss bwd)                     */
+  CLIPN_EPI_SIGLIP = 8,     /* softplus / sigmoid epilogue for SigLipLoss (loss.py:351-367): see
+                               clipn_siglip_* below                                                       */
+};
+
+typedef struct clipn_gemm_desc {
+  const void* a; int64_t lda; int32_t a_mn_major;
+  const void* b; int64_t ldb; int32_t b_mn_major;
+  void* c; int64_t ldc;
+  void* c2; int64_t ldc2;
+  const void* bias;              /* bf16 [N] or NULL */
+  const void* aux; int64_t ldaux; /* bf16 [M,N] residual / pre-activation, or NULL */
+  int32_t m, n, k;
+  int32_t epilogue;              /* enum clipn_epilogue */
+  float alpha;
+  int32_t splits;                /* split-K factor, >=1 (only with CLIPN_EPI_ACCUM_F32) */
+  /* loss epilogues (LSE / CLIP_DLOGITS / SIGLIP); ignored otherwise */
+  const float* row_lse;          /* [M] */
+  const float* col_lse;          /* [N] */
+  float* part_max; float* part_sum; /* [2*ceil(N/BN) * M] each; BN from clipn_gemm_tile_n() */
+  float* pos;                    /* [M] label logit */
+  float* scalar_acc;             /* [2] fp32 accumulators: d logit_scale (raw, pre-chain), d logit_bias */
+  float logit_bias;              /* added to alpha*acc before exp (0 if none) */
+  float gscale;                  /* gradient scale, e.g. 1/(2B) */
+  float col_w;                   /* weight of the column-softmax term (1 with gather_with_grad, 0 w/o) */
+  int32_t label_offset;          /* rank*B for local_loss (loss.py:82-83) */
+  int32_t negative_only;         /* SIGLIP: no positives in this block (loss.py:344-348) */
+} clipn_gemm_desc;
+
+int clipn_gemm(const clipn_gemm_desc* d, clipn_stream_t stream);
+/* CUDA-core restatement of the same contract (same epilogues) used only by the tests to bisect
+ * the tensor-core path. Never on the product path. */
+int clipn_gemm_ref(const clipn_gemm_desc* d, clipn_stream_t stream);
+/* N-tile width the tensor-core kernel will use for this N (sizes the LSE partial buffers). */
+int clipn_gemm_tile_n(int n);
+
+/* ---- LayerNorm (layers.py:11-26, eps 1e-5; fp32 statistics, bf16 in/out) --------------------- */
+int clipn_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                        int64_t rows, int32_t d, float eps, clipn_stream_t stream);
+/* dx_out = (dx_resid ? dx_resid : 0) + LN'(dy); dgamma/dbeta are fp32 accumulators (+=). */
+int clipn_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        const void* dx_resid, void* dx_out, float* dgamma, float* dbeta, int64_t rows, int32_t d,
+                        clipn_stream_t stream);
+
+/* ---- attention core (F.scaled_dot_product_attention, transformer.py:223-228) ------------------
+ * qkv: bf16 [B*L, 3*H*64] (q | k | v, head-major inside each third, as produced by the QKV GEMM);
+ * out: bf16 [B*L, H*64] (heads merged, transformer.py:244); lse: fp32 [B,H,L].
+ * causal != 0 reproduces the additive -inf upper-triangular mask (transformer.py:1716-1722). */
+int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
+                        int32_t causal, float scale, clipn_stream_t stream);
+int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                        int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
+                        clipn_stream_t stream);
+
+/* ---- embeddings / pooling / normalize ----------------------------------------------------------- */
+/* conv1 (kernel = stride = patch, no bias; transformer.py:632-638,794-796) as im2row: image NCHW bf16
+ * [B,3,H,W] -> patches bf16 [B*gh*gw, 3*P*P], column order (c, py, px) == conv1.weight.flatten(1). */
+int clipn_patchify(const void* image, void* patches, int32_t batch, int32_t chans, int32_t height, int32_t width,
+                   int32_t patch, clipn_stream_t stream);
+/* x[b,0,:] = bf16(bf16(cls)+bf16(pos[0])); x[b,1+p,:] = bf16(patch_out[b*np+p] + bf16(pos[1+p]))
+ * (transformer.py:799-801) */
+int clipn_vision_embed_fwd(const void* patch_out, const float* cls, const float* pos, void* x, int32_t batch,
+                           int32_t npatch, int32_t d, clipn_stream_t stream);
+/* dpatch_out (bf16) = dx[:,1:,:]; dcls (f32, +=) = sum_b dx[b,0]; dpos (f32, +=) = sum_b dx[b] */
+int clipn_vision_embed_bwd(const void* dx, void* dpatch_out, float* dcls, float* dpos, int32_t batch, int32_t npatch,
+                           int32_t d, clipn_stream_t stream);
+/* x = bf16(bf16(table[ids]) + bf16(pos))   (model.py:399-401); also eot_idx[b] = argmax_l ids[b,l]
+ * (transformer.py:941-944; first maximal index like torch.argmax) when eot_idx != NULL */
+int clipn_text_embed_fwd(const int64_t* ids, const float* table, const float* pos, void* x, int32_t* eot_idx,
+                         int32_t batch, int32_t seq, int32_t d, int32_t vocab, clipn_stream_t stream);
+/* dtable (f32, +=) scatter-add of dx rows; dpos (f32, +=) = sum_b dx[b] */
+int clipn_text_embed_bwd(const int64_t* ids, const void* dx, float* dtable, float* dpos, int32_t batch, int32_t seq,
+                         int32_t d, int32_t vocab, clipn_stream_t stream);
+/* out[b,:] = x[b*seq + idx[b], :] (idx == NULL -> row 0: CLS pooling transformer.py:787) */
+int clipn_gather_rows(const void* x, const int32_t* idx, void* out, int32_t batch, int32_t seq, int32_t d,
+                      clipn_stream_t stream);
+/* dx (bf16 [B*seq, d]) = 0 except dx[b*seq + idx[b]] = dpooled[b] */
+int clipn_scatter_rows(const void* dpooled, const int32_t* idx, void* dx, int32_t batch, int32_t seq, int32_t d,
+                       clipn_stream_t stream);
+/* F.normalize(x, dim=-1) (model.py:391,411): y = x / max(||x||, 1e-12); inv_norm saved (fp32 [rows]) */
+int clipn_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int32_t d, clipn_stream_t stream);
+/* dx = inv_norm * (dy - y * <dy, y>) ; dy fp32 or bf16 by dy_is_f32 */
+int clipn_l2norm_bwd(const void* dy, int32_t dy_is_f32, const void* y, const float* inv_norm, void* dx, int64_t rows,
+                     int32_t d, clipn_stream_t stream);
+
+/* ---- small reductions / casts ------------------------------------------------------------------ */
+/* out (f32 [n], +=) = column sums of x (bf16 [rows, n])  — bias gradients */
+int clipn_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int32_t n, clipn_stream_t stream);
+int clipn_cast_f32_to_bf16(const float* x, void* y, int64_t n, clipn_stream_t stream);
+
+/* ---- contrastive losses --------------------------------------------------------------------------
+ * ClipLoss (loss.py:57-141), local_loss form: this rank's B rows against all N = W*B columns.
+ * `feats_cols` lists W device pointers (peer-mapped for other ranks: the all-gather of
+ * gather_features loss.py:29-54 is replaced by direct NVLink reads inside the GEMM's TMA loads), each
+ * bf16 [B,E].  Computes row LSE + label logit for one direction:
+ *   lse[m] = logsumexp_n( scale * rows[m] . cols[n] ),  pos[m] = scale * rows[m] . cols[label_offset+m]
+ * workspace: fp32, at least clipn_clip_lse_workspace(B, N) elements. */
+int64_t clipn_clip_lse_workspace(int32_t b, int32_t n);
+int clipn_clip_lse_fwd(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
+                       float scale, int32_t label_offset, float* lse, float* pos, float* workspace,
+                       clipn_stream_t stream);
+/* dlogits (bf16 [B,N]) for one direction, see CLIPN_EPI_CLIP_DLOGITS; col_lse is the OTHER direction's
+ * global LSE vector [N] (all ranks), scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
+int clipn_clip_dlogits(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
+                       float scale, int32_t label_offset, const float* row_lse, const float* col_lse, float col_w,
+                       float gscale, void* dlogits, float* scalar_acc, clipn_stream_t stream);
+/* d_rows (f32 [B,E]) (+)= alpha * dlogits[B,N] @ concat(feats_cols)[N,E] */
+int clipn_clip_dfeat(const void* dlogits, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
+                     float alpha, float* d_rows, clipn_stream_t stream);
+
+/* SigLipLoss block (loss.py:351-367): loss_acc[0] += sum softplus-form loss of one [B x B] block,
+ * dlogits (bf16 [B,B], optional) = d loss/d logits * gscale, scalar_acc[0]/[1] += d scale / d bias. */
+int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, float scale, float bias,
+                       int32_t negative_only, float gscale, float* loss_acc, void* dlogits, float* scalar_acc,
+                       float* workspace, clipn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPN_H_ */

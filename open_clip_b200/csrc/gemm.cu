@@ -1,0 +1,572 @@
+// tcgen05 / TMEM / TMA GEMM family for the CLIP towers and the contrastive-loss logits.
+//
+// One persistent, warp-specialised kernel (1 CTA per SM, 384 threads):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-6 stage mbarrier ring)
+//   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16,
+//                                 fp32 accumulators double-buffered in TMEM: 2 x BN columns)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global)
+// Operands may be K-major (torch Linear layout) or MN-major (weight-gradient / `x @ W` layouts); the
+// MN-major case uses the canonical ((8,n),(8,k)) SW128 layout with LBO = 8 KiB between 64-wide MN groups.
+// The B operand may be split across up to 8 tensor maps (one per rank's peer-mapped feature buffer), which
+// is how the all-gather of gather_features (loss.py:29-54) is fused into the logits GEMM.
+//
+// Replaces (reference, cuBLASLt via ATen): transformer.py:195-197,246,295-299,794,923; model.py:409;
+// loss.py:102-110 and the autograd dgrad/wgrad of each.
+#include <math.h>
+
+#include "common.cuh"
+#include "gemm_internal.cuh"
+
+namespace clipn {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 128 + kEpiWarps * 32;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Epilogues. Each epilogue thread owns one output row; it receives 32 consecutive columns at a time.
+// ---------------------------------------------------------------------------------------------------
+struct EpiState {
+  float run_max, run_sum, pos, acc0, acc1;
+  bool has_pos;
+};
+
+__device__ __forceinline__ void epi_begin(EpiState& st) {
+  st.run_max = -INFINITY;
+  st.run_sum = 0.f;
+  st.pos = 0.f;
+  st.has_pos = false;
+  st.acc0 = 0.f;
+  st.acc1 = 0.f;
+}
+
+__device__ __forceinline__ void store_bf16_row32(void* base, int64_t ld, int row, int col, const float (&v)[32]) {
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + static_cast<int64_t>(row) * ld + col);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[i * 8 + j];
+    dst[i] = pack_bf16x8(t);
+  }
+}
+__device__ __forceinline__ void load_bf16_row32(const void* base, int64_t ld, int row, int col, float (&v)[32]) {
+  const uint4* src =
+      reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + static_cast<int64_t>(row) * ld + col);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+    unpack_bf16x8(__ldg(src + i), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i * 8 + j] = t[j];
+  }
+}
+__device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b)[32]) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bias) + col);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+    unpack_bf16x8(__ldg(src + i), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[i * 8 + j] = t[j];
+  }
+}
+
+// row/col are global output coordinates; caller guarantees col < N (warp-uniform), row may be >= M.
+template <int EPI>
+__device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col, float (&v)[32], EpiState& st) {
+  const bool row_ok = row < p.m;
+  if constexpr (EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_STORE_F32) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+    if (p.bias != nullptr) {
+      float b[32];
+      load_bias32(p.bias, col, b);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += b[i];
+    }
+    if (row_ok) {
+      if constexpr (EPI == CLIPN_EPI_STORE) {
+        store_bf16_row32(p.c, p.ldc, row, col, v);
+      } else {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
+    }
+  } else if constexpr (EPI == CLIPN_EPI_BIAS_GELU) {
+    float b[32];
+    load_bias32(p.bias, col, b);
+    float g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = bf16_round(v[i] + b[i]);
+      g[i] = gelu_exact(v[i]);
+    }
+    if (row_ok) {
+      store_bf16_row32(p.c, p.ldc, row, col, v);
+      store_bf16_row32(p.c2, p.ldc2, row, col, g);
+    }
+  } else if constexpr (EPI == CLIPN_EPI_BIAS_RESID) {
+    float b[32];
+    load_bias32(p.bias, col, b);
+    if (row_ok) {
+      float r[32];
+      load_bf16_row32(p.aux, p.ldaux, row, col, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + b[i]) + r[i];
+      store_bf16_row32(p.c, p.ldc, row, col, v);
+    }
+  } else if constexpr (EPI == CLIPN_EPI_DGELU) {
+    if (row_ok) {
+      float h[32], g[32];
+      load_bf16_row32(p.aux, p.ldaux, row, col, h);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = v[i] * gelu_grad(h[i]);
+        g[i] = gelu_exact(h[i]);
+      }
+      store_bf16_row32(p.c, p.ldc, row, col, v);
+      store_bf16_row32(p.c2, p.ldc2, row, col, g);
+    }
+  } else if constexpr (EPI == CLIPN_EPI_ACCUM_F32) {
+    if (row_ok) {
+      float* dst = reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i] * p.alpha);
+    }
+  } else if constexpr (EPI == CLIPN_EPI_LSE) {
+    const int label = row + p.label_offset;
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = v[i] * p.alpha + p.logit_bias;
+      cmax = fmaxf(cmax, v[i]);
+      if (col + i == label) {
+        st.pos = v[i];
+        st.has_pos = true;
+      }
+    }
+    const float nmax = fmaxf(st.run_max, cmax);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += exp2f((v[i] - nmax) * kLog2e);
+    st.run_sum = st.run_sum * exp2f((st.run_max - nmax) * kLog2e) + s;
+    st.run_max = nmax;
+  } else if constexpr (EPI == CLIPN_EPI_CLIP_DLOGITS) {
+    const int label = row + p.label_offset;
+    const float rl = row_ok ? __ldg(p.row_lse + row) : 0.f;
+    float g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float s = v[i] * p.alpha + p.logit_bias;
+      const float pr = exp2f((s - rl) * kLog2e);
+      const float pc = (p.col_w != 0.f) ? p.col_w * exp2f((s - __ldg(p.col_lse + col + i)) * kLog2e) : 0.f;
+      const float onehot = (col + i == label) ? 1.f : 0.f;
+      g[i] = p.gscale * (pr + pc - (1.f + p.col_w) * onehot);
+      if (row_ok) {
+        st.acc0 += (pr - onehot) * v[i];
+        st.acc1 += (pr - onehot);
+      }
+    }
+    if (row_ok) store_bf16_row32(p.c, p.ldc, row, col, g);
+  } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
+    float g[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float z = v[i] * p.alpha + p.logit_bias;
+      const float y = (!p.negative_only && (col + i == row + p.label_offset)) ? 1.f : -1.f;
+      const float yz = y * z;
+      // -logsigmoid(yz) = softplus(-yz) = max(-yz,0) + log1p(exp(-|yz|))
+      const float e = __expf(-fabsf(yz));
+      const float loss = fmaxf(-yz, 0.f) + log1pf(e);
+      // d/dz = -y * sigmoid(-yz)
+      const float sig = (yz >= 0.f) ? e / (1.f + e) : 1.f / (1.f + e);
+      const float dz = -y * sig;
+      g[i] = p.gscale * dz;
+      if (row_ok) {
+        st.run_sum += loss;
+        st.acc0 += dz * v[i];
+        st.acc1 += dz;
+      }
+    }
+    if (row_ok && p.c != nullptr) store_bf16_row32(p.c, p.ldc, row, col, g);
+  }
+}
+
+// called once per (row, n-slab) after all chunks; `slab` = n_tile*2 + half. Warp-convergent.
+template <int EPI>
+__device__ __forceinline__ void epi_finish(const GemmParams& p, int row, int slab, EpiState& st) {
+  if constexpr (EPI == CLIPN_EPI_LSE) {
+    if (row < p.m) {
+      p.part_max[static_cast<int64_t>(slab) * p.m + row] = st.run_max;
+      p.part_sum[static_cast<int64_t>(slab) * p.m + row] = st.run_sum;
+      if (st.has_pos) p.pos[row] = st.pos;
+    }
+  } else if constexpr (EPI == CLIPN_EPI_CLIP_DLOGITS) {
+    const float a0 = warp_sum(st.acc0), a1 = warp_sum(st.acc1);
+    if (lane_id() == 0 && p.scalar_acc != nullptr) {
+      atomicAdd(p.scalar_acc + 0, a0 * p.gscale);
+      atomicAdd(p.scalar_acc + 1, a1 * p.gscale);
+    }
+  } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
+    const float l = warp_sum(st.run_sum), a0 = warp_sum(st.acc0), a1 = warp_sum(st.acc1);
+    if (lane_id() == 0) {
+      if (p.part_sum != nullptr) atomicAdd(p.part_sum, l * p.gscale);
+      if (p.scalar_acc != nullptr) {
+        atomicAdd(p.scalar_acc + 0, a0 * p.gscale);
+        atomicAdd(p.scalar_acc + 1, a1 * p.gscale);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The tensor-core kernel
+// ---------------------------------------------------------------------------------------------------
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full = empty_bar + Cfg::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm.a);
+    for (int i = 0; i < p.b_maps; ++i) tma_prefetch_desc(&tm.b[i]);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < Cfg::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_work = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int tile = w / p.splits;
+        const int m0 = (tile / p.tiles_n) * BM;
+        const int n0 = (tile % p.tiles_n) * BN;
+        const int kb0 = static_cast<int>((static_cast<int64_t>(split) * p.kblocks) / p.splits);
+        const int kb1 = static_cast<int>((static_cast<int64_t>(split + 1) * p.kblocks) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tm.a, &full_bar[stage], kb * BK, m0);
+          } else {
+            tma_load_2d(sa, &tm.a, &full_bar[stage], m0, kb * BK);
+            tma_load_2d(sa + 8192, &tm.a, &full_bar[stage], m0 + 64, kb * BK);
+          }
+          if (!p.b_mn) {
+            const int map = n0 / p.b_rows_per_map;
+            tma_load_2d(sb, &tm.b[map], &full_bar[stage], kb * BK, n0 - map * p.b_rows_per_map);
+          } else {
+            const int map = (kb * BK) / p.b_rows_per_map;
+            const int krow = kb * BK - map * p.b_rows_per_map;
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(sb + i * 8192, &tm.b[map], &full_bar[stage], n0 + 64 * i, krow);
+          }
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int kb0 = static_cast<int>((static_cast<int64_t>(split) * p.kblocks) / p.splits);
+        const int kb1 = static_cast<int>((static_cast<int64_t>(split + 1) * p.kblocks) / p.splits);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = p.a_mn ? umma_smem_desc(sa + k * 2048, 8192, 1024) : umma_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + k * 2048, 8192, 1024) : umma_smem_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;
+    const int q = e & 3;   // TMEM lane quarter == warp % 4
+    const int h = e >> 2;  // column half of the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int tile = w / p.splits;
+      const int tn = tile % p.tiles_n;
+      const int m0 = (tile / p.tiles_n) * BM;
+      const int n0 = tn * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      EpiState st;
+      epi_begin(st);
+#pragma unroll 1
+      for (int j = 0; j < BN / 64; ++j) {
+        const int cl = h * (BN / 2) + j * 32;
+        float v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cl, v);
+        if (n0 + cl < p.n) epi_apply<EPI>(p, row, n0 + cl, v, st);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      epi_finish<EPI>(p, row, tn * 2 + h, st);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CUDA-core restatement (tests only): identical slab structure and epilogues, no tensor cores.
+// grid = (ceil(M/128), tiles_n*2), block = 128 threads (thread == row).
+// ---------------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void gemm_ref_kernel(const GemmParams p, RefOperands ops, int bn) {
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  const int slab = blockIdx.y;
+  const int n_begin = (slab >> 1) * bn + (slab & 1) * (bn / 2);
+  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(ops.a);
+  EpiState st;
+  epi_begin(st);
+  for (int cl = 0; cl < bn / 2; cl += 32) {
+    const int col = n_begin + cl;
+    if (col >= p.n) break;
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    if (row < p.m) {
+      for (int k = 0; k < p.k; ++k) {
+        const float a = __bfloat162float(p.a_mn ? A[static_cast<int64_t>(k) * ops.lda + row]
+                                                  : A[static_cast<int64_t>(row) * ops.lda + k]);
+        for (int i = 0; i < 32; ++i) {
+          const int n = col + i;
+          float b;
+          if (!p.b_mn) {
+            const int map = n / p.b_rows_per_map;
+            b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                ops.b[map])[static_cast<int64_t>(n - map * p.b_rows_per_map) * ops.ldb + k]);
+          } else {
+            const int map = k / p.b_rows_per_map;
+            b = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(
+                ops.b[map])[static_cast<int64_t>(k - map * p.b_rows_per_map) * ops.ldb + n]);
+          }
+          v[i] += a * b;
+        }
+      }
+    }
+    epi_apply<EPI>(p, row, col, v, st);
+  }
+  epi_finish<EPI>(p, row, slab, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+int gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : 128; }
+
+template <int BN, int EPI>
+static int launch_tc(const TmapSet& tm, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = TileCfg<BN>;
+  static bool configured = false;  // benign race: idempotent attribute set
+  if (!configured) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tc_kernel<BN, EPI><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(tm, p);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+template <int EPI>
+static int launch_ref(const GemmParams& p, const RefOperands& ops, int bn, cudaStream_t stream) {
+  dim3 grid((p.m + 127) / 128, p.tiles_n * 2);
+  gemm_ref_kernel<EPI><<<grid, 128, 0, stream>>>(p, ops, bn);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+#define CLIPN_DISPATCH_EPI(EPIVAR, MACRO)                                   \
+  switch (EPIVAR) {                                                         \
+    case CLIPN_EPI_STORE: MACRO(CLIPN_EPI_STORE); break;                   \
+    case CLIPN_EPI_BIAS_GELU: MACRO(CLIPN_EPI_BIAS_GELU); break;           \
+    case CLIPN_EPI_BIAS_RESID: MACRO(CLIPN_EPI_BIAS_RESID); break;         \
+    case CLIPN_EPI_DGELU: MACRO(CLIPN_EPI_DGELU); break;                   \
+    case CLIPN_EPI_ACCUM_F32: MACRO(CLIPN_EPI_ACCUM_F32); break;           \
+    case CLIPN_EPI_STORE_F32: MACRO(CLIPN_EPI_STORE_F32); break;           \
+    case CLIPN_EPI_LSE: MACRO(CLIPN_EPI_LSE); break;                       \
+    case CLIPN_EPI_CLIP_DLOGITS: MACRO(CLIPN_EPI_CLIP_DLOGITS); break;     \
+    case CLIPN_EPI_SIGLIP: MACRO(CLIPN_EPI_SIGLIP); break;                 \
+    default: return set_error_arg("unknown epilogue", __FILE__, __LINE__); \
+  }
+
+int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps, int64_t b_rows_per_map, bool use_ref,
+                cudaStream_t stream) {
+  CLIPN_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem");
+  CLIPN_REQUIRE(d.n % 32 == 0, "gemm: N must be a multiple of 32");
+  CLIPN_REQUIRE(d.k % 8 == 0 && d.lda % 8 == 0 && d.ldb % 8 == 0, "gemm: K / leading dims must be multiples of 8");
+  CLIPN_REQUIRE(b_maps >= 1 && b_maps <= kMaxBMaps, "gemm: 1..8 B maps");
+  const int ep = d.epilogue;
+  const bool needs_c = !(ep == CLIPN_EPI_LSE || (ep == CLIPN_EPI_SIGLIP && d.c == nullptr));
+  if (needs_c) CLIPN_REQUIRE(d.c != nullptr && d.ldc % 8 == 0, "gemm: C missing or ldc not a multiple of 8");
+  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU)
+    CLIPN_REQUIRE(d.c2 != nullptr && d.ldc2 % 8 == 0, "gemm: C2 required");
+  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID) CLIPN_REQUIRE(d.bias != nullptr, "gemm: bias required");
+  if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU)
+    CLIPN_REQUIRE(d.aux != nullptr && d.ldaux % 8 == 0, "gemm: aux required");
+  if (ep == CLIPN_EPI_LSE) CLIPN_REQUIRE(d.part_max && d.part_sum && d.pos, "gemm: LSE buffers required");
+  if (ep == CLIPN_EPI_CLIP_DLOGITS) CLIPN_REQUIRE(d.row_lse && (d.col_w == 0.f || d.col_lse), "gemm: lse vectors");
+
+  GemmParams p;
+  p.m = d.m; p.n = d.n; p.k = d.k;
+  p.a_mn = d.a_mn_major ? 1 : 0;
+  p.b_mn = d.b_mn_major ? 1 : 0;
+  const int bn = gemm_tile_n(d.n);
+  p.tiles_m = (d.m + BM - 1) / BM;
+  p.tiles_n = (d.n + bn - 1) / bn;
+  p.kblocks = (d.k + BK - 1) / BK;
+  p.splits = (ep == CLIPN_EPI_ACCUM_F32 && d.splits > 1) ? d.splits : 1;
+  if (p.splits > p.kblocks) p.splits = p.kblocks;
+  p.b_maps = b_maps;
+  p.b_rows_per_map = b_maps > 1 ? static_cast<int>(b_rows_per_map) : 0x40000000;
+  if (b_maps > 1) {
+    CLIPN_REQUIRE(b_rows_per_map % bn == 0 || p.b_mn, "gemm: per-rank rows must be a multiple of the N tile");
+    CLIPN_REQUIRE(b_rows_per_map % BK == 0 || !p.b_mn, "gemm: per-rank rows must be a multiple of 64");
+  }
+  p.c = d.c; p.ldc = d.ldc; p.c2 = d.c2; p.ldc2 = d.ldc2;
+  p.bias = d.bias; p.aux = d.aux; p.ldaux = d.ldaux;
+  p.alpha = d.alpha;
+  p.row_lse = d.row_lse; p.col_lse = d.col_lse; p.part_max = d.part_max; p.part_sum = d.part_sum; p.pos = d.pos;
+  p.scalar_acc = d.scalar_acc; p.logit_bias = d.logit_bias; p.gscale = d.gscale; p.col_w = d.col_w;
+  p.label_offset = d.label_offset; p.negative_only = d.negative_only;
+
+  if (use_ref) {
+    RefOperands ops;
+    ops.a = d.a; ops.lda = d.lda; ops.ldb = d.ldb;
+    for (int i = 0; i < kMaxBMaps; ++i) ops.b[i] = b_ptrs[i < b_maps ? i : 0];
+#define CLIPN_REF_CASE(E) return launch_ref<E>(p, ops, bn, stream)
+    CLIPN_DISPATCH_EPI(ep, CLIPN_REF_CASE)
+#undef CLIPN_REF_CASE
+    return CLIPN_OK;
+  }
+
+  int cc_major = 0, sms = 0, cc_minor = 0;
+  clipn_device_info(&sms, &cc_major, &cc_minor);
+  CLIPN_REQUIRE(cc_major == 10, "gemm: the tcgen05 kernels require an sm_100 (B200) device");
+
+  TmapSet tm;
+  int rc;
+  if (!p.a_mn) rc = make_tmap_2d(&tm.a, d.a, 2, d.k, d.m, d.lda * 2, BK, BM, 128);
+  else rc = make_tmap_2d(&tm.a, d.a, 2, d.m, d.k, d.lda * 2, 64, BK, 128);
+  if (rc) return rc;
+  for (int i = 0; i < b_maps; ++i) {
+    if (!p.b_mn) {
+      const uint64_t rows = b_maps > 1 ? static_cast<uint64_t>(b_rows_per_map) : static_cast<uint64_t>(d.n);
+      rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.k, rows, d.ldb * 2, BK, bn, 128);
+    } else {
+      const uint64_t rows = b_maps > 1 ? static_cast<uint64_t>(b_rows_per_map) : static_cast<uint64_t>(d.k);
+      rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.n, rows, d.ldb * 2, 64, BK, 128);
+    }
+    if (rc) return rc;
+  }
+#define CLIPN_TC_CASE(E) \
+  return (bn == 256) ? launch_tc<256, E>(tm, p, stream) : launch_tc<128, E>(tm, p, stream)
+  CLIPN_DISPATCH_EPI(ep, CLIPN_TC_CASE)
+#undef CLIPN_TC_CASE
+  return CLIPN_OK;
+}
+
+}  // namespace clipn
+
+extern "C" int clipn_gemm(const clipn_gemm_desc* d, clipn_stream_t stream) {
+  if (d == nullptr) return clipn::set_error_arg("gemm: null descriptor", __FILE__, __LINE__);
+  const void* b[1] = {d->b};
+  return clipn::gemm_launch(*d, b, 1, 0, false, static_cast<cudaStream_t>(stream));
+}
+extern "C" int clipn_gemm_ref(const clipn_gemm_desc* d, clipn_stream_t stream) {
+  if (d == nullptr) return clipn::set_error_arg("gemm: null descriptor", __FILE__, __LINE__);
+  const void* b[1] = {d->b};
+  return clipn::gemm_launch(*d, b, 1, 0, true, static_cast<cudaStream_t>(stream));
+}
+extern "C" int clipn_gemm_tile_n(int n) { return clipn::gemm_tile_n(n); }
