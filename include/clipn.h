@@ -89,6 +89,10 @@ typedef struct clipn_gemm_desc {
   float col_w;                   /* weight of the column-softmax term (1 with gather_with_grad, 0 w/o) */
   int32_t label_offset;          /* rank*B for local_loss (loss.py:82-83) */
   int32_t negative_only;         /* SIGLIP: no positives in this block (loss.py:344-348) */
+  /* optional DEVICE scalars (fp32), so callers never sync to read logit_scale / logit_bias on the host:
+     effective alpha = alpha * (*alpha_dev), effective logit_bias = logit_bias + (*logit_bias_dev) */
+  const float* alpha_dev;
+  const float* logit_bias_dev;
 } clipn_gemm_desc;
 
 int clipn_gemm(const clipn_gemm_desc* d, clipn_stream_t stream);
@@ -161,22 +165,23 @@ int clipn_cast_f32_to_bf16(const float* x, void* y, int64_t n, clipn_stream_t st
  * workspace: fp32, at least clipn_clip_lse_workspace(B, N) elements. */
 int64_t clipn_clip_lse_workspace(int32_t b, int32_t n);
 int clipn_clip_lse_fwd(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                       float scale, int32_t label_offset, float* lse, float* pos, float* workspace,
-                       clipn_stream_t stream);
+                       float scale, const float* scale_dev, int32_t label_offset, float* lse, float* pos,
+                       float* workspace, clipn_stream_t stream);
 /* dlogits (bf16 [B,N]) for one direction, see CLIPN_EPI_CLIP_DLOGITS; col_lse is the OTHER direction's
  * global LSE vector [N] (all ranks), scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
 int clipn_clip_dlogits(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                       float scale, int32_t label_offset, const float* row_lse, const float* col_lse, float col_w,
-                       float gscale, void* dlogits, float* scalar_acc, clipn_stream_t stream);
-/* d_rows (f32 [B,E]) (+)= alpha * dlogits[B,N] @ concat(feats_cols)[N,E] */
+                       float scale, const float* scale_dev, int32_t label_offset, const float* row_lse,
+                       const float* col_lse, float col_w, float gscale, void* dlogits, float* scalar_acc,
+                       clipn_stream_t stream);
+/* d_rows ([B,E], fp32 if out_is_f32 else bf16) = alpha * dlogits[B,N] @ concat(feats_cols)[N,E] */
 int clipn_clip_dfeat(const void* dlogits, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                     float alpha, float* d_rows, clipn_stream_t stream);
+                     float alpha, const float* alpha_dev, void* d_rows, int32_t out_is_f32, clipn_stream_t stream);
 
 /* SigLipLoss block (loss.py:351-367): loss_acc[0] += sum softplus-form loss of one [B x B] block,
  * dlogits (bf16 [B,B], optional) = d loss/d logits * gscale, scalar_acc[0]/[1] += d scale / d bias. */
-int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, float scale, float bias,
-                       int32_t negative_only, float gscale, float* loss_acc, void* dlogits, float* scalar_acc,
-                       float* workspace, clipn_stream_t stream);
+int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, const float* scale_dev,
+                       const float* bias_dev, int32_t negative_only, float gscale, float* loss_acc, void* dlogits,
+                       float* scalar_acc, clipn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -240,8 +240,11 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, int row, int sla
 // ---------------------------------------------------------------------------------------------------
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
   using Cfg = TileCfg<BN>;
+  GemmParams p = p_in;
+  if (p.alpha_dev != nullptr) p.alpha *= __ldg(p.alpha_dev);
+  if (p.logit_bias_dev != nullptr) p.logit_bias += __ldg(p.logit_bias_dev);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
@@ -400,7 +403,10 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p) {
 // grid = (ceil(M/128), tiles_n*2), block = 128 threads (thread == row).
 // ---------------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void gemm_ref_kernel(const GemmParams p, RefOperands ops, int bn) {
+__global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) {
+  GemmParams p = p_in;
+  if (p.alpha_dev != nullptr) p.alpha *= __ldg(p.alpha_dev);
+  if (p.logit_bias_dev != nullptr) p.logit_bias += __ldg(p.logit_bias_dev);
   const int row = blockIdx.x * 128 + threadIdx.x;
   const int slab = blockIdx.y;
   const int n_begin = (slab >> 1) * bn + (slab & 1) * (bn / 2);
@@ -485,7 +491,8 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
                 cudaStream_t stream) {
   CLIPN_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem");
   CLIPN_REQUIRE(d.n % 32 == 0, "gemm: N must be a multiple of 32");
-  CLIPN_REQUIRE(d.k % 8 == 0 && d.lda % 8 == 0 && d.ldb % 8 == 0, "gemm: K / leading dims must be multiples of 8");
+  CLIPN_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "gemm: leading dims must be multiples of 8");
+  CLIPN_REQUIRE(d.k % 8 == 0 || (d.a_mn_major && d.b_mn_major), "gemm: K must be a multiple of 8 for K-major operands");
   CLIPN_REQUIRE(b_maps >= 1 && b_maps <= kMaxBMaps, "gemm: 1..8 B maps");
   const int ep = d.epilogue;
   const bool needs_c = !(ep == CLIPN_EPI_LSE || (ep == CLIPN_EPI_SIGLIP && d.c == nullptr));
@@ -520,6 +527,7 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   p.row_lse = d.row_lse; p.col_lse = d.col_lse; p.part_max = d.part_max; p.part_sum = d.part_sum; p.pos = d.pos;
   p.scalar_acc = d.scalar_acc; p.logit_bias = d.logit_bias; p.gscale = d.gscale; p.col_w = d.col_w;
   p.label_offset = d.label_offset; p.negative_only = d.negative_only;
+  p.alpha_dev = d.alpha_dev; p.logit_bias_dev = d.logit_bias_dev;
 
   if (use_ref) {
     RefOperands ops;

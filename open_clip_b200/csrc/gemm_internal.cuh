@@ -25,6 +25,7 @@ struct GemmParams {
   float* part_max; float* part_sum; float* pos; float* scalar_acc;
   float logit_bias, gscale, col_w;
   int label_offset, negative_only;
+  const float* alpha_dev; const float* logit_bias_dev;
 };
 
 struct RefOperands {

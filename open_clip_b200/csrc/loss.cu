@@ -25,12 +25,13 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
   lse[row] = mx + __logf(sum);
 }
 
-static void base_desc(clipn_gemm_desc& d, const void* rows, int b, int n, int e, float scale) {
+static void base_desc(clipn_gemm_desc& d, const void* rows, int b, int n, int e, float scale,
+                      const float* scale_dev) {
   memset(&d, 0, sizeof(d));
   d.a = rows; d.lda = e; d.a_mn_major = 0;
   d.ldb = e; d.b_mn_major = 0;
   d.m = b; d.n = n; d.k = e;
-  d.alpha = scale; d.splits = 1;
+  d.alpha = scale; d.alpha_dev = scale_dev; d.splits = 1;
 }
 
 }  // namespace clipn
@@ -44,15 +45,15 @@ extern "C" int64_t clipn_clip_lse_workspace(int32_t b, int32_t n) {
 }
 
 extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b,
-                                  int32_t e, float scale, int32_t label_offset, float* lse, float* pos,
-                                  float* workspace, clipn_stream_t stream) {
+                                  int32_t e, float scale, const float* scale_dev, int32_t label_offset, float* lse,
+                                  float* pos, float* workspace, clipn_stream_t stream) {
   CLIPN_REQUIRE(feats_rows && feats_cols && lse && pos && workspace, "clip_lse_fwd: null pointer");
   CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_lse_fwd: world must be 1..8");
   const int n = world * b;
   const int bn = gemm_tile_n(n);
   const int slabs = 2 * ((n + bn - 1) / bn);
   clipn_gemm_desc d;
-  base_desc(d, feats_rows, b, n, e, scale);
+  base_desc(d, feats_rows, b, n, e, scale, scale_dev);
   d.b = feats_cols[0];
   d.epilogue = CLIPN_EPI_LSE;
   d.part_max = workspace;
@@ -67,14 +68,14 @@ extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* const* fea
 }
 
 extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b,
-                                  int32_t e, float scale, int32_t label_offset, const float* row_lse,
-                                  const float* col_lse, float col_w, float gscale, void* dlogits, float* scalar_acc,
+                                  int32_t e, float scale, const float* scale_dev, int32_t label_offset,
+                                  const float* row_lse, const float* col_lse, float col_w, float gscale, void* dlogits, float* scalar_acc,
                                   clipn_stream_t stream) {
   CLIPN_REQUIRE(feats_rows && feats_cols && row_lse && dlogits, "clip_dlogits: null pointer");
   CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_dlogits: world must be 1..8");
   const int n = world * b;
   clipn_gemm_desc d;
-  base_desc(d, feats_rows, b, n, e, scale);
+  base_desc(d, feats_rows, b, n, e, scale, scale_dev);
   d.b = feats_cols[0];
   d.epilogue = CLIPN_EPI_CLIP_DLOGITS;
   d.c = dlogits; d.ldc = n;
@@ -85,7 +86,8 @@ extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* const* fea
 }
 
 extern "C" int clipn_clip_dfeat(const void* dlogits, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                                float alpha, float* d_rows, clipn_stream_t stream) {
+                                float alpha, const float* alpha_dev, void* d_rows, int32_t out_is_f32,
+                                clipn_stream_t stream) {
   CLIPN_REQUIRE(dlogits && feats_cols && d_rows, "clip_dfeat: null pointer");
   CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_dfeat: world must be 1..8");
   const int n = world * b;
@@ -95,22 +97,21 @@ extern "C" int clipn_clip_dfeat(const void* dlogits, const void* const* feats_co
   d.b = feats_cols[0]; d.ldb = e; d.b_mn_major = 1;  // each rank: [B(K rows), E] -> MN-major
   d.c = d_rows; d.ldc = e;
   d.m = b; d.n = e; d.k = n;
-  d.alpha = alpha; d.splits = 1;
-  d.epilogue = CLIPN_EPI_STORE_F32;
+  d.alpha = alpha; d.alpha_dev = alpha_dev; d.splits = 1;
+  d.epilogue = out_is_f32 ? CLIPN_EPI_STORE_F32 : CLIPN_EPI_STORE;
   return gemm_launch(d, feats_cols, world, b, false, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, float scale, float bias,
-                                  int32_t negative_only, float gscale, float* loss_acc, void* dlogits,
-                                  float* scalar_acc, float* workspace, clipn_stream_t stream) {
-  (void)workspace;
-  CLIPN_REQUIRE(img && txt && loss_acc, "siglip_block: null pointer");
+extern "C" int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, const float* scale_dev,
+                                  const float* bias_dev, int32_t negative_only, float gscale, float* loss_acc,
+                                  void* dlogits, float* scalar_acc, clipn_stream_t stream) {
+  CLIPN_REQUIRE(img && txt && loss_acc && scale_dev, "siglip_block: null pointer");
   clipn_gemm_desc d;
-  base_desc(d, img, b, b, e, scale);
+  base_desc(d, img, b, b, e, 1.0f, scale_dev);
   d.b = txt;
   d.epilogue = CLIPN_EPI_SIGLIP;
   d.c = dlogits; d.ldc = b;
-  d.logit_bias = bias;
+  d.logit_bias = 0.f; d.logit_bias_dev = bias_dev;
   d.negative_only = negative_only;
   d.gscale = gscale;
   d.part_sum = loss_acc;

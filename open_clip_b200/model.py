@@ -1,0 +1,305 @@
+"""NativeCLIP — drop-in for the reference `CLIP` module (model.py:318-548) on B200.
+
+Same constructor surface that matters to callers (embed_dim, vision_cfg, text_cfg, init_logit_scale,
+init_logit_bias, output_dict), same parameter names / shapes / dtypes as `--precision bf16`
+(convert_weights_to_lp model.py:738-765: Linear/conv/in_proj/projection weights bf16, LayerNorm affine,
+embeddings and logit_scale fp32) so checkpoints round-trip, same forward/encode_* contracts
+ — but every FLOP of the towers runs in libclipn.so (sm_100a kernels) and the backward is
+scheduled by hand in tower.py (one autograd.Function per tower).
+
+There is no CPU path: calling this on CPU tensors raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops, tower
+from ._lib import ClipnError
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _is_lowp(name: str) -> bool:
+    """convert_weights_to_lp (model.py:738-765) targets."""
+    return name in ("text_projection", "visual.proj", "visual.conv1.weight") or ".attn." in name or ".mlp." in name
+
+
+class _Node(nn.Module):
+    """Pure parameter container used to reproduce the reference's module tree / state_dict names."""
+
+
+class _VisualNode(_Node):
+    def __init__(self, image_size: int):
+        super().__init__()
+        self.image_size = (image_size, image_size)  # image_text_task.py:44 reads visual.image_size
+
+    def no_weight_decay(self):
+        return {"positional_embedding", "class_embedding"}  # transformer.py:778-781
+
+
+def _block_node(d: int, mlp: int) -> _Node:
+    b = _Node()
+    b.ln_1, b.ln_2, b.attn, b.mlp = _Node(), _Node(), _Node(), _Node()
+    b.attn.out_proj, b.mlp.c_fc, b.mlp.c_proj = _Node(), _Node(), _Node()
+    for ln in (b.ln_1, b.ln_2):
+        ln.weight = nn.Parameter(torch.ones(d))
+        ln.bias = nn.Parameter(torch.zeros(d))
+    b.attn.in_proj_weight = nn.Parameter(torch.empty(3 * d, d))
+    b.attn.in_proj_bias = nn.Parameter(torch.zeros(3 * d))
+    b.attn.out_proj.weight = nn.Parameter(torch.empty(d, d))
+    b.attn.out_proj.bias = nn.Parameter(torch.zeros(d))
+    b.mlp.c_fc.weight = nn.Parameter(torch.empty(mlp, d))
+    b.mlp.c_fc.bias = nn.Parameter(torch.zeros(mlp))
+    b.mlp.c_proj.weight = nn.Parameter(torch.empty(d, mlp))
+    b.mlp.c_proj.bias = nn.Parameter(torch.zeros(d))
+    return b
+
+
+def _transformer_node(d: int, layers: int, mlp_ratio: float) -> _Node:
+    t = _Node()
+    t.resblocks = nn.ModuleList([_block_node(d, int(d * mlp_ratio)) for _ in range(layers)])
+    return t
+
+
+class _TowerFn(torch.autograd.Function):
+    """One tower = one autograd node. forward(inputs, *params) -> features; backward -> every param grad."""
+
+    @staticmethod
+    def forward(ctx, model: "NativeCLIP", which: str, normalize: bool, inp: torch.Tensor, *params):
+        names = model._tower_param_names[which]
+        P = dict(zip(names, params))
+        cfg = model._vcfg if which == "visual" else model._tcfg
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        fwd = tower.vision_forward if which == "visual" else tower.text_forward
+        feat, saved = fwd(P, cfg, inp, normalize, model._scratch[which], need_grad)
+        ctx.model, ctx.which, ctx.saved, ctx.P, ctx.names = model, which, saved, P, names
+        return feat
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        model, which, P, names = ctx.model, ctx.which, ctx.P, ctx.names
+        if ctx.saved is None:
+            raise ClipnError("backward through a NativeCLIP tower that ran without saved activations")
+        cfg = model._vcfg if which == "visual" else model._tcfg
+        arena = model._grad_arena(which)
+        arena["flat32"].zero_()
+        G = arena["views32"]
+        bwd = tower.vision_backward if which == "visual" else tower.text_backward
+        bwd(P, G, cfg, ctx.saved, dfeat, model._scratch[which])
+        ctx.saved = None
+        # bf16 params get bf16 grads (one cast over the contiguous low-precision segment)
+        n_lowp = arena["n_lowp"]
+        if n_lowp:
+            ops.cast_f32_to_bf16(arena["flat32"][:n_lowp], out=arena["flat16"])
+        grads = []
+        for n, p in zip(names, ctx.P.values()):
+            if not p.requires_grad:
+                grads.append(None)
+            elif p.dtype == BF16:
+                grads.append(arena["views16"][n])
+            else:
+                grads.append(arena["views32"][n])
+        return (None, None, None, None, *grads)
+
+
+class NativeCLIP(nn.Module):
+    def __init__(self, embed_dim: int, vision_cfg: dict, text_cfg: dict, quick_gelu: bool = False,
+                 init_logit_scale: float = math.log(1 / 0.07), init_logit_bias: Optional[float] = None,
+                 output_dict: bool = False, device="cuda"):
+        super().__init__()
+        if quick_gelu:
+            raise ClipnError("NativeCLIP implements nn.GELU (erf); quick_gelu configs are out of scope")
+        v, t = dict(vision_cfg), dict(text_cfg)
+        head_width = v.get("head_width", 64)
+        if head_width != 64 or t["width"] // t["heads"] != 64:
+            raise ClipnError("NativeCLIP kernels are specialised for head_dim 64 (every native open_clip ViT)")
+        self.output_dict = output_dict
+        self.embed_dim = embed_dim
+        self.context_length = t.get("context_length", 77)
+        self.vocab_size = t.get("vocab_size", 49408)
+        vw, tw = v["width"], t["width"]
+        grid = v["image_size"] // v["patch_size"]
+        mlp_ratio = v.get("mlp_ratio", 4.0)
+        self._vcfg = tower.TowerCfg(width=vw, layers=v["layers"], heads=vw // 64, seq=grid * grid + 1, causal=False,
+                                    prefix="visual.transformer", embed_dim=embed_dim, image_size=v["image_size"],
+                                    patch=v["patch_size"])
+        self._tcfg = tower.TowerCfg(width=tw, layers=t["layers"], heads=t["heads"], seq=self.context_length, causal=True,
+                                    prefix="transformer", embed_dim=embed_dim, vocab=self.vocab_size)
+
+        # ---- parameter tree with the reference's names
+        self.visual = _VisualNode(v["image_size"])
+        self.visual.conv1 = _Node()
+        self.visual.conv1.weight = nn.Parameter(torch.empty(vw, 3, v["patch_size"], v["patch_size"]))
+        self.visual.class_embedding = nn.Parameter(torch.empty(vw))
+        self.visual.positional_embedding = nn.Parameter(torch.empty(grid * grid + 1, vw))
+        self.visual.ln_pre, self.visual.ln_post = _Node(), _Node()
+        for ln in (self.visual.ln_pre, self.visual.ln_post):
+            ln.weight = nn.Parameter(torch.ones(vw))
+            ln.bias = nn.Parameter(torch.zeros(vw))
+        self.visual.transformer = _transformer_node(vw, v["layers"], mlp_ratio)
+        self.visual.proj = nn.Parameter(torch.empty(vw, embed_dim))
+        self.transformer = _transformer_node(tw, t["layers"], t.get("mlp_ratio", 4.0))
+        self.token_embedding = _Node()
+        self.token_embedding.weight = nn.Parameter(torch.empty(self.vocab_size, tw))
+        self.positional_embedding = nn.Parameter(torch.empty(self.context_length, tw))
+        self.ln_final = _Node()
+        self.ln_final.weight = nn.Parameter(torch.ones(tw))
+        self.ln_final.bias = nn.Parameter(torch.zeros(tw))
+        self.text_projection = nn.Parameter(torch.empty(tw, embed_dim))
+        self.logit_scale = nn.Parameter(torch.ones([]) * init_logit_scale)
+        self.logit_bias = nn.Parameter(torch.ones([]) * init_logit_bias) if init_logit_bias is not None else None
+        # causal mask is a predicate inside the attention kernel; keep the (non-persistent) buffer for API parity
+        self.register_buffer("attn_mask", torch.full((self.context_length, self.context_length), float("-inf")).triu_(1),
+                             persistent=False)
+
+        self.init_parameters()
+        self._apply_dtype_contract()
+        self.to(device)
+        self._finalize()
+
+    # ------------------------------------------------------------------ construction helpers
+    @torch.no_grad()
+    def init_parameters(self):
+        """Reference init distributions (transformer.py:145-155,1664-1685,641-645,719; model.py:326)."""
+        vw, tw = self._vcfg.width, self._tcfg.width
+        vs = vw ** -0.5
+        nn.init.normal_(self.visual.class_embedding, std=vs)
+        nn.init.normal_(self.visual.positional_embedding, std=vs)
+        nn.init.normal_(self.visual.proj, std=vs)
+        nn.init.kaiming_uniform_(self.visual.conv1.weight, a=math.sqrt(5))
+        for blk in self.visual.transformer.resblocks:  # vision tower keeps torch defaults (+ MHA-style attn init)
+            nn.init.xavier_uniform_(blk.attn.in_proj_weight)
+            for lin in (blk.attn.out_proj, blk.mlp.c_fc, blk.mlp.c_proj):
+                nn.init.kaiming_uniform_(lin.weight, a=math.sqrt(5))
+            for lin in (blk.mlp.c_fc, blk.mlp.c_proj):
+                bound = 1 / math.sqrt(lin.weight.shape[1])
+                nn.init.uniform_(lin.bias, -bound, bound)
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        L = self._tcfg.layers
+        proj_std, attn_std, fc_std = (tw ** -0.5) * ((2 * L) ** -0.5), tw ** -0.5, (2 * tw) ** -0.5
+        for blk in self.transformer.resblocks:
+            nn.init.normal_(blk.attn.in_proj_weight, std=attn_std)
+            nn.init.normal_(blk.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(blk.mlp.c_fc.weight, std=fc_std)
+            nn.init.normal_(blk.mlp.c_proj.weight, std=proj_std)
+            for lin in (blk.mlp.c_fc, blk.mlp.c_proj):
+                bound = 1 / math.sqrt(lin.weight.shape[1])
+                nn.init.uniform_(lin.bias, -bound, bound)
+        nn.init.normal_(self.text_projection, std=tw ** -0.5)
+
+    def _apply_dtype_contract(self):
+        for name, p in self.named_parameters():
+            p.data = p.data.to(BF16 if _is_lowp(name) else F32)
+
+    def _finalize(self):
+        names = [n for n, _ in self.named_parameters()]
+        self._tower_param_names = {
+            "visual": [n for n in names if n.startswith("visual.")],
+            "text": [n for n in names if not n.startswith("visual.") and n not in ("logit_scale", "logit_bias")],
+        }
+        self._scratch = {"visual": tower.Scratch(), "text": tower.Scratch()}
+        self._arenas: Dict[str, dict] = {}
+        self.grad_checkpointing = False
+
+    def _grad_arena(self, which: str) -> dict:
+        """Flat fp32 gradient accumulators for one tower (low-precision params first) + a bf16 shadow."""
+        a = self._arenas.get(which)
+        params = dict(self.named_parameters())
+        names = self._tower_param_names[which]
+        dev = params[names[0]].device
+        if a is None or a["flat32"].device != dev:
+            lowp = [n for n in names if params[n].dtype == BF16]
+            highp = [n for n in names if params[n].dtype != BF16]
+            pad = lambda k: (k + 63) // 64 * 64  # keep every view 256-byte aligned (TMA needs 16)
+            n_lowp = sum(pad(params[n].numel()) for n in lowp)
+            total = n_lowp + sum(pad(params[n].numel()) for n in highp)
+            flat32 = torch.zeros(total, dtype=F32, device=dev)
+            flat16 = torch.empty(n_lowp, dtype=BF16, device=dev)
+            v32, v16, off = {}, {}, 0
+            for n in lowp + highp:
+                k = params[n].numel()
+                v32[n] = flat32[off:off + k].view(params[n].shape)
+                if n in lowp:
+                    v16[n] = flat16[off:off + k].view(params[n].shape)
+                off += pad(k)
+            a = {"flat32": flat32, "flat16": flat16, "views32": v32, "views16": v16, "n_lowp": n_lowp}
+            self._arenas[which] = a
+        return a
+
+    # ------------------------------------------------------------------ reference API surface
+    def set_grad_checkpointing(self, enable: bool = True, impl: str = "inline"):
+        # model.py:377-379. Activation storage here is already 10*d/token with LN/GELU recompute.
+        self.grad_checkpointing = enable
+
+    def lock_image_tower(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
+        for n, p in self.named_parameters():
+            if n.startswith("visual."):
+                p.requires_grad = False
+
+    def lock_text_tower(self, unlocked_layers: int = 0, freeze_layer_norm: bool = True, pooler_in_head: bool = True):
+        for n in self._tower_param_names["text"]:
+            dict(self.named_parameters())[n].requires_grad = False
+
+    def no_weight_decay(self):
+        # model.py:381-387
+        return {"positional_embedding", "visual.positional_embedding", "visual.class_embedding"}
+
+    def _run_tower(self, which: str, inp: torch.Tensor, normalize: bool) -> torch.Tensor:
+        if not inp.is_cuda:
+            raise ClipnError("NativeCLIP runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+        params = dict(self.named_parameters())
+        plist = [params[n] for n in self._tower_param_names[which]]
+        return _TowerFn.apply(self, which, normalize, inp, *plist)
+
+    def encode_image(self, image, normalize: bool = False):
+        return self._run_tower("visual", image, normalize)
+
+    def encode_text(self, text, normalize: bool = False):
+        return self._run_tower("text", text, normalize)
+
+    def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None):
+        # model.py:528-548
+        image_features = self.encode_image(image, normalize=True) if image is not None else None
+        text_features = self.encode_text(text, normalize=True) if text is not None else None
+        if self.output_dict:
+            out = {"image_features": image_features, "text_features": text_features,
+                   "logit_scale": self.logit_scale.exp()}
+            if self.logit_bias is not None:
+                out["logit_bias"] = self.logit_bias.clone()
+            return out
+        if self.logit_bias is not None:
+            return image_features, text_features, self.logit_scale.exp(), self.logit_bias.clone()
+        return image_features, text_features, self.logit_scale.exp()
+
+    # ------------------------------------------------------------------ checkpoints
+    @torch.no_grad()
+    def load_reference_state_dict(self, sd: Dict[str, torch.Tensor]):
+        """Load a reference CLIP state_dict (fp32 or bf16); values are cast to this module's dtype contract."""
+        own = dict(self.named_parameters())
+        missing = [k for k in own if k not in sd]
+        unexpected = [k for k in sd if k not in own and k != "attn_mask"]
+        if missing or unexpected:
+            raise ClipnError(f"state_dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
+        for k, p in own.items():
+            p.copy_(sd[k].to(device=p.device, dtype=p.dtype).view(p.shape))
+
+
+CONFIGS = {
+    "ViT-B-32": dict(embed_dim=512, vision_cfg=dict(image_size=224, layers=12, width=768, patch_size=32),
+                     text_cfg=dict(context_length=77, vocab_size=49408, width=512, heads=8, layers=12)),
+    "ViT-B-16": dict(embed_dim=512, vision_cfg=dict(image_size=224, layers=12, width=768, patch_size=16),
+                     text_cfg=dict(context_length=77, vocab_size=49408, width=512, heads=8, layers=12)),
+    "tiny": dict(embed_dim=128, vision_cfg=dict(image_size=64, layers=2, width=128, patch_size=16),
+                 text_cfg=dict(context_length=20, vocab_size=512, width=128, heads=2, layers=2)),
+}
+
+
+def create_model(name: str, output_dict: bool = True, device="cuda", **kw) -> NativeCLIP:
+    """Counterpart of open_clip.create_model(name, precision='bf16', output_dict=True) (factory.py:264)."""
+    cfg = CONFIGS[name]
+    return NativeCLIP(cfg["embed_dim"], cfg["vision_cfg"], cfg["text_cfg"], output_dict=output_dict, device=device, **kw)

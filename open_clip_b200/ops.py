@@ -1,0 +1,265 @@
+"""Tensor-level wrappers over the C ABI (one function per libclipn entry point).
+
+torch is plumbing here: it owns device memory and the stream; every FLOP runs in libclipn.so.
+All functions enqueue on torch.cuda.current_stream() and never synchronise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise L.ClipnError(f"{name}: expected a CUDA tensor (open_clip_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise L.ClipnError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise L.ClipnError(f"{name}: expected a contiguous tensor")
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, epilogue: int = L.EPI_STORE,
+         bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         out2: Optional[torch.Tensor] = None, alpha: float = 1.0, splits: int = 1, ref: bool = False,
+         **extra) -> torch.Tensor:
+    """C[M,N] = epilogue(alpha * A . B^T); see include/clipn.h for operand layouts.
+    a: [M,K] (a_mn False) or [K,M] (a_mn True); b: [N,K] (b_mn False) or [K,N] (b_mn True)."""
+    _chk(a, BF16, "gemm.a")
+    _chk(b, BF16, "gemm.b")
+    assert a.dim() == 2 and b.dim() == 2
+    M, K = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise L.ClipnError(f"gemm: K mismatch {K} vs {Kb}")
+    f32_out = epilogue in (L.EPI_ACCUM_F32, L.EPI_STORE_F32)
+    if out is None and epilogue not in (L.EPI_LSE,):
+        out = torch.empty((M, N), dtype=F32 if f32_out else BF16, device=a.device)
+    d = L.GemmDesc()
+    d.a, d.lda, d.a_mn_major = a.data_ptr(), a.stride(0), int(a_mn)
+    d.b, d.ldb, d.b_mn_major = b.data_ptr(), b.stride(0), int(b_mn)
+    if out is not None:
+        _chk(out, F32 if f32_out else BF16, "gemm.out")
+        assert tuple(out.shape) == (M, N)
+        d.c, d.ldc = out.data_ptr(), out.stride(0)
+    if out2 is not None:
+        _chk(out2, BF16, "gemm.out2")
+        d.c2, d.ldc2 = out2.data_ptr(), out2.stride(0)
+    if bias is not None:
+        _chk(bias, BF16, "gemm.bias")
+        d.bias = bias.data_ptr()
+    if aux is not None:
+        _chk(aux, BF16, "gemm.aux")
+        d.aux, d.ldaux = aux.data_ptr(), aux.stride(0)
+    d.m, d.n, d.k = M, N, K
+    d.epilogue, d.alpha, d.splits = epilogue, alpha, splits
+    for k, v in extra.items():
+        setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
+    fn = L.lib().clipn_gemm_ref if ref else L.lib().clipn_gemm
+    L.check(fn(C.byref(d), _stream()))
+    return out
+
+
+def wgrad_splits(m_out: int, n_out: int, k: int) -> int:
+    """split-K factor for a weight-gradient GEMM so that tiles*splits ~ 3 waves of 148 SMs."""
+    bn = L.lib().clipn_gemm_tile_n(n_out)
+    tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
+    kblocks = (k + 63) // 64
+    s = max(1, (3 * 148 + tiles - 1) // tiles)
+    return max(1, min(s, kblocks // 4 if kblocks >= 8 else 1))
+
+
+def layernorm_fwd(x, gamma, beta, out=None, eps: float = 1e-5, save_stats: bool = True):
+    _chk(x, BF16, "ln.x"); _chk(gamma, F32, "ln.gamma"); _chk(beta, F32, "ln.beta")
+    rows, d = x.shape
+    y = out if out is not None else torch.empty_like(x)
+    mean = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
+    rstd = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
+    L.check(L.lib().clipn_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
+                                        _ptr(rstd), rows, d, eps, _stream()))
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=None, out=None):
+    _chk(dy, BF16, "lnb.dy"); _chk(x, BF16, "lnb.x")
+    rows, d = x.shape
+    dx = out if out is not None else torch.empty_like(x)
+    L.check(L.lib().clipn_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                        _ptr(resid), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, d, _stream()))
+    return dx
+
+
+def attention_fwd(qkv, batch, seq, heads, causal, out=None):
+    _chk(qkv, BF16, "attn.qkv")
+    d = heads * 64
+    assert tuple(qkv.shape) == (batch * seq, 3 * d)
+    o = out if out is not None else torch.empty((batch * seq, d), dtype=BF16, device=qkv.device)
+    lse = torch.empty((batch, heads, seq), dtype=F32, device=qkv.device)
+    L.check(L.lib().clipn_attention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), batch, seq, heads, int(causal),
+                                        64 ** -0.5, _stream()))
+    return o, lse
+
+
+def attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, out=None):
+    _chk(qkv, BF16, "attnb.qkv"); _chk(o, BF16, "attnb.o"); _chk(do, BF16, "attnb.do"); _chk(lse, F32, "attnb.lse")
+    dqkv = out if out is not None else torch.empty_like(qkv)
+    L.check(L.lib().clipn_attention_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                        batch, seq, heads, int(causal), 64 ** -0.5, _stream()))
+    return dqkv
+
+
+def patchify(image, patch):
+    _chk(image, BF16, "patchify.image")
+    B, Cc, H, W = image.shape
+    out = torch.empty((B * (H // patch) * (W // patch), Cc * patch * patch), dtype=BF16, device=image.device)
+    L.check(L.lib().clipn_patchify(image.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, _stream()))
+    return out
+
+
+def vision_embed_fwd(patch_out, cls, pos, batch, npatch):
+    _chk(patch_out, BF16, "vemb.patch_out"); _chk(cls, F32, "vemb.cls"); _chk(pos, F32, "vemb.pos")
+    d = patch_out.shape[1]
+    x = torch.empty((batch * (npatch + 1), d), dtype=BF16, device=patch_out.device)
+    L.check(L.lib().clipn_vision_embed_fwd(patch_out.data_ptr(), cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch,
+                                           npatch, d, _stream()))
+    return x
+
+
+def vision_embed_bwd(dx, dcls, dpos, batch, npatch):
+    _chk(dx, BF16, "vembb.dx")
+    d = dx.shape[1]
+    dpatch = torch.empty((batch * npatch, d), dtype=BF16, device=dx.device)
+    L.check(L.lib().clipn_vision_embed_bwd(dx.data_ptr(), dpatch.data_ptr(), _ptr(dcls), _ptr(dpos), batch, npatch, d,
+                                           _stream()))
+    return dpatch
+
+
+def text_embed_fwd(ids, table, pos):
+    _chk(ids, torch.int64, "temb.ids"); _chk(table, F32, "temb.table"); _chk(pos, F32, "temb.pos")
+    B, S = ids.shape
+    vocab, d = table.shape
+    x = torch.empty((B * S, d), dtype=BF16, device=ids.device)
+    eot = torch.empty(B, dtype=torch.int32, device=ids.device)
+    L.check(L.lib().clipn_text_embed_fwd(ids.data_ptr(), table.data_ptr(), pos.data_ptr(), x.data_ptr(), eot.data_ptr(),
+                                         B, S, d, vocab, _stream()))
+    return x, eot
+
+
+def text_embed_bwd(ids, dx, dtable, dpos):
+    _chk(ids, torch.int64, "tembb.ids"); _chk(dx, BF16, "tembb.dx"); _chk(dtable, F32, "tembb.dtable")
+    B, S = ids.shape
+    vocab, d = dtable.shape
+    L.check(L.lib().clipn_text_embed_bwd(ids.data_ptr(), dx.data_ptr(), dtable.data_ptr(), _ptr(dpos), B, S, d, vocab,
+                                         _stream()))
+
+
+def gather_rows(x, idx, batch, seq):
+    _chk(x, BF16, "gather.x")
+    d = x.shape[1]
+    out = torch.empty((batch, d), dtype=BF16, device=x.device)
+    L.check(L.lib().clipn_gather_rows(x.data_ptr(), _ptr(idx), out.data_ptr(), batch, seq, d, _stream()))
+    return out
+
+
+def scatter_rows(dpooled, idx, batch, seq, out=None):
+    _chk(dpooled, BF16, "scatter.dpooled")
+    d = dpooled.shape[1]
+    dx = out if out is not None else torch.empty((batch * seq, d), dtype=BF16, device=dpooled.device)
+    L.check(L.lib().clipn_scatter_rows(dpooled.data_ptr(), _ptr(idx), dx.data_ptr(), batch, seq, d, _stream()))
+    return dx
+
+
+def l2norm_fwd(x):
+    _chk(x, BF16, "l2.x")
+    rows, d = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty(rows, dtype=F32, device=x.device)
+    L.check(L.lib().clipn_l2norm_fwd(x.data_ptr(), y.data_ptr(), inv.data_ptr(), rows, d, _stream()))
+    return y, inv
+
+
+def l2norm_bwd(dy, y, inv):
+    assert dy.dtype in (F32, BF16) and dy.is_contiguous() and dy.is_cuda
+    rows, d = y.shape
+    dx = torch.empty_like(y)
+    L.check(L.lib().clipn_l2norm_bwd(dy.data_ptr(), int(dy.dtype == F32), y.data_ptr(), inv.data_ptr(), dx.data_ptr(),
+                                     rows, d, _stream()))
+    return dx
+
+
+def colsum(x, out):
+    _chk(x, BF16, "colsum.x"); _chk(out, F32, "colsum.out")
+    rows, n = x.shape
+    L.check(L.lib().clipn_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), rows, n, _stream()))
+
+
+def cast_f32_to_bf16(x, out=None):
+    _chk(x, F32, "cast.x")
+    y = out if out is not None else torch.empty(x.shape, dtype=BF16, device=x.device)
+    L.check(L.lib().clipn_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+# ---------------------------------------------------------------------------- contrastive loss pieces
+def _ptr_array(ptrs: Sequence[int]):
+    arr = (C.c_void_p * len(ptrs))(*ptrs)
+    return arr
+
+
+def clip_lse_fwd(rows: torch.Tensor, col_ptrs: Sequence[int], scale: torch.Tensor, label_offset: int):
+    """Row log-sum-exp and label logit of scale * rows @ concat(cols).T; cols given as per-rank device pointers.
+    `scale` is a 1-element fp32 DEVICE tensor (no host sync)."""
+    _chk(rows, BF16, "lse.rows"); _chk(scale, F32, "lse.scale")
+    b, e = rows.shape
+    world = len(col_ptrs)
+    ws = torch.empty(L.lib().clipn_clip_lse_workspace(b, world * b), dtype=F32, device=rows.device)
+    lse = torch.empty(b, dtype=F32, device=rows.device)
+    pos = torch.zeros(b, dtype=F32, device=rows.device)
+    L.check(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
+                                       label_offset, lse.data_ptr(), pos.data_ptr(), ws.data_ptr(), _stream()))
+    return lse, pos
+
+
+def clip_dlogits(rows, col_ptrs, scale, label_offset, row_lse, col_lse, col_w, gscale, scalar_acc):
+    _chk(rows, BF16, "dlogits.rows")
+    b, e = rows.shape
+    world = len(col_ptrs)
+    out = torch.empty((b, world * b), dtype=BF16, device=rows.device)
+    L.check(L.lib().clipn_clip_dlogits(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
+                                       label_offset, row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(),
+                                       _ptr(scalar_acc), _stream()))
+    return out
+
+
+def clip_dfeat(dlogits, col_ptrs, e, alpha: torch.Tensor, out_dtype=BF16):
+    _chk(dlogits, BF16, "dfeat.dlogits")
+    b = dlogits.shape[0]
+    world = len(col_ptrs)
+    out = torch.empty((b, e), dtype=out_dtype, device=dlogits.device)
+    L.check(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, alpha.data_ptr(),
+                                     out.data_ptr(), int(out_dtype == F32), _stream()))
+    return out
+
+
+def siglip_block(img, txt, scale, bias, negative_only, gscale, loss_acc, scalar_acc, want_grad: bool):
+    _chk(img, BF16, "siglip.img"); _chk(txt, BF16, "siglip.txt")
+    b, e = img.shape
+    dl = torch.empty((b, b), dtype=BF16, device=img.device) if want_grad else None
+    L.check(L.lib().clipn_siglip_block(img.data_ptr(), txt.data_ptr(), b, e, scale.data_ptr(), bias.data_ptr(),
+                                       int(negative_only), gscale, loss_acc.data_ptr(), _ptr(dl), _ptr(scalar_acc),
+                                       _stream()))
+    return dl

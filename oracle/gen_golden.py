@@ -190,12 +190,15 @@ def main():
     open_clip = _import_reference()
     gold_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold_dir, exist_ok=True)
-    print("model goldens: tiny")
-    torch.save(model_goldens(open_clip, "tiny", batch=6, seed=1, keep_full_grads=False),
-               os.path.join(gold_dir, "tiny_model.pt"))
-    print("model goldens: ViT-B-32")
-    torch.save(model_goldens(open_clip, "ViT-B-32", batch=8, seed=0), os.path.join(gold_dir, "vitb32_model.pt"))
-    for w in (2, 4):
+    only = sys.argv[1:] or ["tiny", "vitb32", "loss"]
+    if "tiny" in only:
+        print("model goldens: tiny")
+        torch.save(model_goldens(open_clip, "tiny", batch=8, seed=1, keep_full_grads=False),
+                   os.path.join(gold_dir, "tiny_model.pt"))
+    if "vitb32" in only:
+        print("model goldens: ViT-B-32")
+        torch.save(model_goldens(open_clip, "ViT-B-32", batch=8, seed=0), os.path.join(gold_dir, "vitb32_model.pt"))
+    for w in ((2, 4) if "loss" in only else ()):
         print(f"loss goldens: world={w}")
         torch.save(loss_goldens(w), os.path.join(gold_dir, f"loss_w{w}.pt"))
     print("done")

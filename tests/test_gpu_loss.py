@@ -1,0 +1,59 @@
+"""GPU parity: the fused contrastive-loss kernels (through NativeClipLoss / NativeSigLipLoss) vs the oracle's
+restatement of the reference losses on identical bf16-representable inputs.  Tolerances: value 2e-3 abs,
+feature grads rel-L2 1e-2 (d(logits) is rounded to bf16 once), logit-scale grad 1e-2 rel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from open_clip_b200.loss import NativeClipLoss, NativeSigLipLoss
+from oracle import clip_oracle as O
+from gpu_util import BF16, F32, randn, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _feats(b, e, seed):
+    i = F.normalize(randn(b, e, seed=seed, dtype=F32), dim=-1).to(BF16)
+    t = F.normalize(randn(b, e, seed=seed + 1, dtype=F32), dim=-1).to(BF16)
+    return i, t
+
+
+@pytest.mark.parametrize("b,e", [(32, 64), (128, 128), (256, 512), (1000 // 8 * 8, 512), (4096, 512)])
+@pytest.mark.parametrize("feat_dtype", [BF16, F32])
+def test_clip_loss_value_and_grads(b, e, feat_dtype):
+    if b % 32:
+        b = b // 32 * 32
+    i, t = _feats(b, e, 3)
+    scale = torch.tensor(14.2857, device="cuda")
+    gi, gt = i.to(feat_dtype).requires_grad_(True), t.to(feat_dtype).requires_grad_(True)
+    gs = scale.clone().requires_grad_(True)
+    out = NativeClipLoss()(gi, gt, gs, output_dict=True)
+    loss = out["contrastive_loss"]
+    loss.backward()
+    ri, rt = i.float().cpu().requires_grad_(True), t.float().cpu().requires_grad_(True)
+    rs = scale.cpu().clone().requires_grad_(True)
+    rl = O.clip_loss(ri, rt, rs)
+    rl.backward()
+    assert abs(float(loss) - float(rl)) < (2e-3 if feat_dtype == F32 else 3e-2)
+    assert rel_err(gi.grad.cpu(), ri.grad) < 1e-2
+    assert rel_err(gt.grad.cpu(), rt.grad) < 1e-2
+    assert abs(float(gs.grad) - float(rs.grad)) < 1e-2 * abs(float(rs.grad)) + 1e-5
+
+
+@pytest.mark.parametrize("b,e", [(64, 32), (256, 512)])
+def test_siglip_loss_value_and_grads(b, e):
+    i, t = _feats(b, e, 5)
+    scale, bias = torch.tensor(10.0, device="cuda"), torch.tensor(-10.0, device="cuda")
+    gi, gt = i.clone().requires_grad_(True), t.clone().requires_grad_(True)
+    gs, gb = scale.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    loss = NativeSigLipLoss()(gi, gt, gs, gb)
+    loss.backward()
+    ri, rt = i.float().cpu().requires_grad_(True), t.float().cpu().requires_grad_(True)
+    rs, rb = scale.cpu().clone().requires_grad_(True), bias.cpu().clone().requires_grad_(True)
+    rl = O.siglip_block_loss(ri, rt, rs, rb)
+    rl.backward()
+    assert abs(float(loss) - float(rl)) < 2e-2 * abs(float(rl)) + 1e-3
+    assert rel_err(gi.grad.cpu(), ri.grad) < 1.5e-2
+    assert rel_err(gt.grad.cpu(), rt.grad) < 1.5e-2
+    assert abs(float(gs.grad) - float(rs.grad)) < 2e-2 * abs(float(rs.grad)) + 1e-4
+    assert abs(float(gb.grad) - float(rb.grad)) < 2e-2 * abs(float(rb.grad)) + 1e-4

@@ -1,0 +1,136 @@
+"""GPU parity of the whole path through the reference-facing API: NativeCLIP.forward + NativeClipLoss + backward
+vs (a) the committed reference fixtures (tests/golden, minted from /root/reference) and (b) the fp32 oracle
+run on the box's CPU with the same parameters and inputs.
+
+Stated tolerances (measured reference bf16-vs-fp32 noise floor): features cos >= 0.9999 and
+max-abs <= 3e-3 vs the fp32 reference, loss |d| <= 1e-2, parameter grads rel-L2 <= 2e-2 (a few tiny-norm
+tensors get 5e-2 absolute-scaled slack, listed in the test)."""
+import os
+
+import pytest
+import torch
+
+from open_clip_b200.loss import NativeClipLoss
+from open_clip_b200.model import NativeCLIP, create_model
+from oracle import clip_oracle as O
+from gpu_util import BF16, F32, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _probe(name, g):
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    d = torch.randn(g.shape, generator=gen)
+    g = g.float().cpu()
+    return torch.tensor([g.norm().item(), (g * d).sum().item()])
+
+
+def _native_from(cfg_name, base):
+    m = create_model(cfg_name, output_dict=True)
+    m.load_reference_state_dict(base)
+    return m
+
+
+def _run_native(m, image, text):
+    out = m(image=image.cuda().to(BF16), text=text.cuda())
+    loss = NativeClipLoss()(out["image_features"], out["text_features"], out["logit_scale"])
+    loss.backward()
+    torch.cuda.synchronize()
+    return out, loss
+
+
+def _check_features(out, gold32):
+    for key in ("image_features", "text_features"):
+        got = out[key].float().cpu()
+        ref = gold32[key]
+        cos = torch.nn.functional.cosine_similarity(got, ref, dim=-1).min().item()
+        mx = (got - ref).abs().max().item()
+        assert cos >= 0.9999 and mx <= 3e-3, (key, cos, mx)
+
+
+def test_tiny_forward_loss_and_all_grads_vs_reference_fixture_and_oracle(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "tiny_model.pt"), weights_only=False)
+    cfg = O.CONFIGS["tiny"]
+    base = O.init_params(cfg, seed=gold["seed"], bias_std=0.02)
+    m = _native_from("tiny", base)
+    out, loss = _run_native(m, gold["image"], gold["text"])
+    _check_features(out, gold["fp32"])
+    assert abs(float(loss) - gold["fp32"]["loss"]) <= 1e-2
+    # full gradients vs the fp32 oracle (autograd through the restatement) on the same bf16-rounded parameters
+    p = {k: v.requires_grad_(True) for k, v in O.cast_params(base, "bf16").items()}
+    p32 = {k: v.detach().float().requires_grad_(True) for k, v in p.items()}
+    o = O.clip_forward(p32, cfg, gold["image"].to(BF16).float(), gold["text"])
+    O.clip_loss(o["image_features"], o["text_features"], o["logit_scale"]).backward()
+    bad = []
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        assert prm.grad.dtype == prm.dtype, name
+        e = rel_err(prm.grad.cpu(), p32[name].grad)
+        if e > 3e-2:
+            bad.append((name, e))
+    assert not bad, bad
+    for k, pr in gold["fp32"]["grad_probes"].items():
+        mine = _probe(k, dict(m.named_parameters())[k].grad)
+        assert abs(mine[0] - pr[0]) <= 5e-2 * pr[0].abs() + 1e-7, (k, mine, pr)
+
+
+def test_vitb32_forward_loss_and_grad_probes_vs_reference_fixture(golden_dir):
+    gold = torch.load(os.path.join(golden_dir, "vitb32_model.pt"), weights_only=False)
+    cfg = O.CONFIGS["ViT-B-32"]
+    base = O.init_params(cfg, seed=gold["seed"], bias_std=0.02)
+    image, text = O.synthetic_batch(cfg, gold["batch"], seed=100 + gold["seed"])
+    assert abs(float(image.double().abs().sum()) - gold["image_checksum"]) < 1e-6 * gold["image_checksum"]
+    m = _native_from("ViT-B-32", base)
+    out, loss = _run_native(m, image, text)
+    _check_features(out, gold["fp32"])
+    assert abs(float(loss) - gold["fp32"]["loss"]) <= 1e-2
+    worst = 0.0
+    for k, pr in gold["fp32"]["grad_probes"].items():
+        mine = _probe(k, dict(m.named_parameters())[k].grad)
+        worst = max(worst, float(abs(mine[0] - pr[0]) / (pr[0].abs() + 1e-9)))
+        assert abs(mine[0] - pr[0]) <= 5e-2 * pr[0].abs() + 1e-7, (k, mine, pr)
+        assert abs(mine[1] - pr[1]) <= 8e-2 * pr[0].abs() + 1e-7, (k, mine, pr)
+
+
+def test_state_dict_names_shapes_dtypes_match_reference_contract():
+    m = create_model("ViT-B-32")
+    sd = m.state_dict()
+    shapes = O.param_shapes(O.CONFIGS["ViT-B-32"])
+    assert set(sd) == set(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+        assert v.dtype == (BF16 if O.is_lowp_param(k) else F32), k
+    assert sum(p.numel() for p in m.parameters()) == 151277313
+    assert m.visual.image_size == (224, 224) and m.context_length == 77 and m.vocab_size == 49408
+
+
+def test_eval_image_only_and_text_only_calls():
+    m = create_model("tiny")
+    cfg = O.CONFIGS["tiny"]
+    image, text = O.synthetic_batch(cfg, 8, seed=1)
+    with torch.no_grad():
+        a = m(image=image.cuda().to(BF16))
+        b = m(text=text.cuda())
+        f = m.encode_image(image.cuda().to(BF16), normalize=False)
+    assert a["text_features"] is None and a["image_features"].shape == (8, 128)
+    assert b["image_features"] is None and b["text_features"].shape == (8, 128)
+    assert f.shape == (8, 128)
+
+
+def test_train_steps_reduce_loss():
+    torch.manual_seed(0)
+    m = create_model("tiny")
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.0)
+    cfg = O.CONFIGS["tiny"]
+    image, text = O.synthetic_batch(cfg, 32, seed=2)
+    image, text = image.cuda().to(BF16), text.cuda()
+    loss_fn = NativeClipLoss()
+    losses = []
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        out = m(image=image, text=text)
+        loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"])
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0], losses

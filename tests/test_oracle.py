@@ -1,0 +1,96 @@
+"""CPU suite: the oracle against the committed golden fixtures (minted from the real reference by
+oracle/gen_golden.py) and against the reference's own pinned identity (tests/test_siglip_chunked_loss.py)."""
+import os
+
+import pytest
+import torch
+
+from oracle import clip_oracle as O
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _probe(name, g):
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    d = torch.randn(g.shape, generator=gen)
+    g = g.float()
+    return torch.tensor([g.norm().item(), (g * d).sum().item()])
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_tiny_model_matches_reference_fixture(golden_dir, prec):
+    gold = _load(golden_dir, "tiny_model.pt")
+    cfg = O.CONFIGS["tiny"]
+    base = O.init_params(cfg, seed=gold["seed"], bias_std=0.02)
+    assert abs(float(sum(v.double().abs().sum() for v in base.values())) - gold["param_checksum"]) < 1e-6 * gold["param_checksum"]
+    p = {k: v.requires_grad_(True) for k, v in O.cast_params(base, prec).items()}
+    image = gold["image"].to(torch.bfloat16 if prec == "bf16" else torch.float32)
+    out = O.clip_forward(p, cfg, image, gold["text"])
+    loss = O.clip_loss(out["image_features"], out["text_features"], out["logit_scale"])
+    loss.backward()
+    g = gold[prec]
+    tol = 1e-6 if prec == "fp32" else 2e-2
+    assert (out["image_features"].float() - g["image_features"]).abs().max() <= tol
+    assert (out["text_features"].float() - g["text_features"]).abs().max() <= tol
+    assert abs(float(loss) - g["loss"]) <= (1e-5 if prec == "fp32" else 2e-2)
+    for k, pr in g["grad_probes"].items():
+        mine = _probe(k, p[k].grad)
+        assert abs(mine[0] - pr[0]) <= (1e-4 if prec == "fp32" else 5e-2) * (pr[0].abs() + 1e-6), k
+
+
+def test_vitb32_fp32_features_match_reference_fixture(golden_dir):
+    gold = _load(golden_dir, "vitb32_model.pt")
+    cfg = O.CONFIGS["ViT-B-32"]
+    base = O.init_params(cfg, seed=gold["seed"], bias_std=0.02)
+    image, text = O.synthetic_batch(cfg, gold["batch"], seed=100 + gold["seed"])
+    assert abs(float(image.double().abs().sum()) - gold["image_checksum"]) < 1e-6 * gold["image_checksum"]
+    with torch.no_grad():
+        out = O.clip_forward(base, cfg, image, text)
+        loss = O.clip_loss(out["image_features"], out["text_features"], out["logit_scale"])
+    g = gold["fp32"]
+    assert (out["image_features"] - g["image_features"]).abs().max() <= 1e-5
+    assert (out["text_features"] - g["text_features"]).abs().max() <= 1e-5
+    assert abs(float(loss) - g["loss"]) <= 1e-5
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_rank_losses_match_gloo_reference_fixture(golden_dir, world):
+    gold = _load(golden_dir, f"loss_w{world}.pt")
+    f = gold["feats"]
+    for case in gold["cases"]:
+        img = [t.clone().requires_grad_(True) for t in f["img"]]
+        txt = [t.clone().requires_grad_(True) for t in f["txt"]]
+        scale = f["scale"].clone().requires_grad_(True)
+        if case["kind"] == "clip":
+            losses = O.clip_loss_ranks(img, txt, scale, case["kwargs"]["local_loss"], case["kwargs"]["gather_with_grad"])
+        else:
+            losses = O.siglip_loss_ranks(img, txt, scale, f["bias"].clone().requires_grad_(True))
+        sum(losses).backward()
+        for r in range(world):
+            assert abs(float(losses[r]) - case["ranks"][r]["loss"]) < 1e-5
+            assert (img[r].grad - case["ranks"][r]["d_img"]).abs().max() < 1e-6
+            assert (txt[r].grad - case["ranks"][r]["d_txt"]).abs().max() < 1e-6
+
+
+def test_siglip_chunked_identity():
+    """The one value identity the reference's own tests pin for this path (tests/test_siglip_chunked_loss.py):
+    softplus form with a diagonal correction == labels form.  B=64, D=32, scale 10, bias -10, atol 1e-5."""
+    g = torch.Generator().manual_seed(0)
+    img = torch.nn.functional.normalize(torch.randn(64, 32, generator=g), dim=-1)
+    txt = torch.nn.functional.normalize(torch.randn(64, 32, generator=g), dim=-1)
+    scale, bias = torch.tensor(10.0), torch.tensor(-10.0)
+    full = O.siglip_block_loss(img, txt, scale, bias)
+    logits = scale * img @ txt.T + bias
+    chunked = (torch.nn.functional.softplus(logits).sum() - logits.diag().sum()) / 64
+    assert abs(float(full) - float(chunked)) < 1e-5
+    neg = O.siglip_block_loss(img, txt, scale, bias, negative_only=True)
+    assert abs(float(neg) - float(torch.nn.functional.softplus(logits).sum() / 64)) < 1e-5
+
+
+def test_cpu_trainer_steps_and_loss_decreases():
+    tr = O.CpuTrainer(O.CONFIGS["tiny"], seed=0, lr=1e-3)
+    image, text = O.synthetic_batch(O.CONFIGS["tiny"], 8, seed=3)
+    losses = [tr.step(image, text) for _ in range(4)]
+    assert losses[-1] < losses[0]
