@@ -36,8 +36,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 
-#ifndef CLIPN_SPIN_LIMIT
-#define CLIPN_SPIN_LIMIT (1u << 27)
+#ifndef CLIPN_WAIT_CYCLES
+#define CLIPN_WAIT_CYCLES 10000000000LL
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -85,9 +85,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > CLIPN_SPIN_LIMIT) {
+    if (clock64() - t0 > CLIPN_WAIT_CYCLES) {  // ~5 s at 2 GHz: a legitimate wait is micro- to milliseconds
       printf("clipn: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, (void*)bar, parity);
       __trap();

@@ -54,33 +54,36 @@ __device__ __forceinline__ void epi_begin(EpiState& st) {
   st.acc1 = 0.f;
 }
 
-__device__ __forceinline__ void store_bf16_row32(void* base, int64_t ld, int row, int col, const float (&v)[32]) {
+// nvalid = number of valid columns in this 32-wide chunk (multiple of 8; N-tail support)
+__device__ __forceinline__ void store_bf16_row32(void* base, int64_t ld, int row, int col, const float (&v)[32],
+                                                 int nvalid) {
   uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(base) + static_cast<int64_t>(row) * ld + col);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = v[i * 8 + j];
-    dst[i] = pack_bf16x8(t);
+    if (i * 8 < nvalid) dst[i] = pack_bf16x8(t);
   }
 }
-__device__ __forceinline__ void load_bf16_row32(const void* base, int64_t ld, int row, int col, float (&v)[32]) {
+__device__ __forceinline__ void load_bf16_row32(const void* base, int64_t ld, int row, int col, float (&v)[32],
+                                                int nvalid) {
   const uint4* src =
       reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + static_cast<int64_t>(row) * ld + col);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float t[8];
-    unpack_bf16x8(__ldg(src + i), t);
+    unpack_bf16x8((i * 8 < nvalid) ? __ldg(src + i) : make_uint4(0, 0, 0, 0), t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[i * 8 + j] = t[j];
   }
 }
-__device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b)[32]) {
+__device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b)[32], int nvalid) {
   const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(bias) + col);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float t[8];
-    unpack_bf16x8(__ldg(src + i), t);
+    unpack_bf16x8((i * 8 < nvalid) ? __ldg(src + i) : make_uint4(0, 0, 0, 0), t);
 #pragma unroll
     for (int j = 0; j < 8; ++j) b[i * 8 + j] = t[j];
   }
@@ -90,27 +93,29 @@ __device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b
 template <int EPI>
 __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col, float (&v)[32], EpiState& st) {
   const bool row_ok = row < p.m;
+  const int nvalid = (p.n - col) < 32 ? (p.n - col) : 32;
   if constexpr (EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_STORE_F32) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
     if (p.bias != nullptr) {
       float b[32];
-      load_bias32(p.bias, col, b);
+      load_bias32(p.bias, col, b, nvalid);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += b[i];
     }
     if (row_ok) {
       if constexpr (EPI == CLIPN_EPI_STORE) {
-        store_bf16_row32(p.c, p.ldc, row, col, v);
+        store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
       } else {
         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          if (i * 4 < nvalid) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
       }
     }
   } else if constexpr (EPI == CLIPN_EPI_BIAS_GELU) {
     float b[32];
-    load_bias32(p.bias, col, b);
+    load_bias32(p.bias, col, b, nvalid);
     float g[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -118,43 +123,44 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
       g[i] = gelu_exact(v[i]);
     }
     if (row_ok) {
-      store_bf16_row32(p.c, p.ldc, row, col, v);
-      store_bf16_row32(p.c2, p.ldc2, row, col, g);
+      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
+      store_bf16_row32(p.c2, p.ldc2, row, col, g, nvalid);
     }
   } else if constexpr (EPI == CLIPN_EPI_BIAS_RESID) {
     float b[32];
-    load_bias32(p.bias, col, b);
+    load_bias32(p.bias, col, b, nvalid);
     if (row_ok) {
       float r[32];
-      load_bf16_row32(p.aux, p.ldaux, row, col, r);
+      load_bf16_row32(p.aux, p.ldaux, row, col, r, nvalid);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + b[i]) + r[i];
-      store_bf16_row32(p.c, p.ldc, row, col, v);
+      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
     }
   } else if constexpr (EPI == CLIPN_EPI_DGELU) {
     if (row_ok) {
       float h[32], g[32];
-      load_bf16_row32(p.aux, p.ldaux, row, col, h);
+      load_bf16_row32(p.aux, p.ldaux, row, col, h, nvalid);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         v[i] = v[i] * gelu_grad(h[i]);
         g[i] = gelu_exact(h[i]);
       }
-      store_bf16_row32(p.c, p.ldc, row, col, v);
-      store_bf16_row32(p.c2, p.ldc2, row, col, g);
+      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
+      store_bf16_row32(p.c2, p.ldc2, row, col, g, nvalid);
     }
   } else if constexpr (EPI == CLIPN_EPI_ACCUM_F32) {
     if (row_ok) {
       float* dst = reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dst + i, v[i] * p.alpha);
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) atomicAdd(dst + i, v[i] * p.alpha);
     }
   } else if constexpr (EPI == CLIPN_EPI_LSE) {
     const int label = row + p.label_offset;
     float cmax = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      v[i] = v[i] * p.alpha + p.logit_bias;
+      v[i] = (i < nvalid) ? v[i] * p.alpha + p.logit_bias : -INFINITY;
       cmax = fmaxf(cmax, v[i]);
       if (col + i == label) {
         st.pos = v[i];
@@ -175,15 +181,16 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
     for (int i = 0; i < 32; ++i) {
       const float s = v[i] * p.alpha + p.logit_bias;
       const float pr = exp2f((s - rl) * kLog2e);
-      const float pc = (p.col_w != 0.f) ? p.col_w * exp2f((s - __ldg(p.col_lse + col + i)) * kLog2e) : 0.f;
+      const float pc =
+          (p.col_w != 0.f && i < nvalid) ? p.col_w * exp2f((s - __ldg(p.col_lse + col + i)) * kLog2e) : 0.f;
       const float onehot = (col + i == label) ? 1.f : 0.f;
       g[i] = p.gscale * (pr + pc - (1.f + p.col_w) * onehot);
-      if (row_ok) {
+      if (row_ok && i < nvalid) {
         st.acc0 += (pr - onehot) * v[i];
         st.acc1 += (pr - onehot);
       }
     }
-    if (row_ok) store_bf16_row32(p.c, p.ldc, row, col, g);
+    if (row_ok) store_bf16_row32(p.c, p.ldc, row, col, g, nvalid);
   } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
     float g[32];
 #pragma unroll
@@ -198,13 +205,13 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
       const float sig = (yz >= 0.f) ? e / (1.f + e) : 1.f / (1.f + e);
       const float dz = -y * sig;
       g[i] = p.gscale * dz;
-      if (row_ok) {
+      if (row_ok && i < nvalid) {
         st.run_sum += loss;
         st.acc0 += dz * v[i];
         st.acc1 += dz;
       }
     }
-    if (row_ok && p.c != nullptr) store_bf16_row32(p.c, p.ldc, row, col, g);
+    if (row_ok && p.c != nullptr) store_bf16_row32(p.c, p.ldc, row, col, g, nvalid);
   }
 }
 
@@ -490,7 +497,7 @@ static int launch_ref(const GemmParams& p, const RefOperands& ops, int bn, cudaS
 int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps, int64_t b_rows_per_map, bool use_ref,
                 cudaStream_t stream) {
   CLIPN_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem");
-  CLIPN_REQUIRE(d.n % 32 == 0, "gemm: N must be a multiple of 32");
+  CLIPN_REQUIRE(d.n % 8 == 0, "gemm: N must be a multiple of 8");
   CLIPN_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "gemm: leading dims must be multiples of 8");
   CLIPN_REQUIRE(d.k % 8 == 0 || (d.a_mn_major && d.b_mn_major), "gemm: K must be a multiple of 8 for K-major operands");
   CLIPN_REQUIRE(b_maps >= 1 && b_maps <= kMaxBMaps, "gemm: 1..8 B maps");

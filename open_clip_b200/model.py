@@ -69,11 +69,10 @@ class _TowerFn(torch.autograd.Function):
     """One tower = one autograd node. forward(inputs, *params) -> features; backward -> every param grad."""
 
     @staticmethod
-    def forward(ctx, model: "NativeCLIP", which: str, normalize: bool, inp: torch.Tensor, *params):
+    def forward(ctx, model: "NativeCLIP", which: str, normalize: bool, need_grad: bool, inp: torch.Tensor, *params):
         names = model._tower_param_names[which]
         P = dict(zip(names, params))
         cfg = model._vcfg if which == "visual" else model._tcfg
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         fwd = tower.vision_forward if which == "visual" else tower.text_forward
         feat, saved = fwd(P, cfg, inp, normalize, model._scratch[which], need_grad)
         ctx.model, ctx.which, ctx.saved, ctx.P, ctx.names = model, which, saved, P, names
@@ -103,7 +102,7 @@ class _TowerFn(torch.autograd.Function):
                 grads.append(arena["views16"][n])
             else:
                 grads.append(arena["views32"][n])
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class NativeCLIP(nn.Module):
@@ -254,7 +253,9 @@ class NativeCLIP(nn.Module):
             raise ClipnError("NativeCLIP runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
         params = dict(self.named_parameters())
         plist = [params[n] for n in self._tower_param_names[which]]
-        return _TowerFn.apply(self, which, normalize, inp, *plist)
+        # grad mode is always off inside Function.forward, so decide here whether activations must be saved
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
+        return _TowerFn.apply(self, which, normalize, need_grad, inp, *plist)
 
     def encode_image(self, image, normalize: bool = False):
         return self._run_tower("visual", image, normalize)

@@ -16,6 +16,18 @@ BF16 = torch.bfloat16
 F32 = torch.float32
 
 
+# instrumentation used by bench.py: kernel-launch counter and CUDA events around one GEMM signature
+LAUNCHES = 0
+PROFILE_KEY = None          # (M, N, K, epilogue) or None
+PROFILE_EVENTS = []         # [(start_event, end_event)] recorded on the launching stream
+
+
+def _call(rc: int, n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+    L.check(rc)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -70,7 +82,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     for k, v in extra.items():
         setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
     fn = L.lib().clipn_gemm_ref if ref else L.lib().clipn_gemm
-    L.check(fn(C.byref(d), _stream()))
+    if PROFILE_KEY is not None and PROFILE_KEY == (M, N, K, epilogue):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _call(fn(C.byref(d), _stream()))
+        e1.record()
+        PROFILE_EVENTS.append((e0, e1))
+    else:
+        _call(fn(C.byref(d), _stream()))
     return out
 
 
@@ -89,7 +108,7 @@ def layernorm_fwd(x, gamma, beta, out=None, eps: float = 1e-5, save_stats: bool 
     y = out if out is not None else torch.empty_like(x)
     mean = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
     rstd = torch.empty(rows, dtype=F32, device=x.device) if save_stats else None
-    L.check(L.lib().clipn_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
+    _call(L.lib().clipn_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean),
                                         _ptr(rstd), rows, d, eps, _stream()))
     return y, mean, rstd
 
@@ -98,7 +117,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=None, out=None)
     _chk(dy, BF16, "lnb.dy"); _chk(x, BF16, "lnb.x")
     rows, d = x.shape
     dx = out if out is not None else torch.empty_like(x)
-    L.check(L.lib().clipn_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+    _call(L.lib().clipn_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                         _ptr(resid), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, d, _stream()))
     return dx
 
@@ -109,7 +128,7 @@ def attention_fwd(qkv, batch, seq, heads, causal, out=None):
     assert tuple(qkv.shape) == (batch * seq, 3 * d)
     o = out if out is not None else torch.empty((batch * seq, d), dtype=BF16, device=qkv.device)
     lse = torch.empty((batch, heads, seq), dtype=F32, device=qkv.device)
-    L.check(L.lib().clipn_attention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), batch, seq, heads, int(causal),
+    _call(L.lib().clipn_attention_fwd(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), batch, seq, heads, int(causal),
                                         64 ** -0.5, _stream()))
     return o, lse
 
@@ -117,7 +136,7 @@ def attention_fwd(qkv, batch, seq, heads, causal, out=None):
 def attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, out=None):
     _chk(qkv, BF16, "attnb.qkv"); _chk(o, BF16, "attnb.o"); _chk(do, BF16, "attnb.do"); _chk(lse, F32, "attnb.lse")
     dqkv = out if out is not None else torch.empty_like(qkv)
-    L.check(L.lib().clipn_attention_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+    _call(L.lib().clipn_attention_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                         batch, seq, heads, int(causal), 64 ** -0.5, _stream()))
     return dqkv
 
@@ -126,7 +145,7 @@ def patchify(image, patch):
     _chk(image, BF16, "patchify.image")
     B, Cc, H, W = image.shape
     out = torch.empty((B * (H // patch) * (W // patch), Cc * patch * patch), dtype=BF16, device=image.device)
-    L.check(L.lib().clipn_patchify(image.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, _stream()))
+    _call(L.lib().clipn_patchify(image.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, _stream()))
     return out
 
 
@@ -134,7 +153,7 @@ def vision_embed_fwd(patch_out, cls, pos, batch, npatch):
     _chk(patch_out, BF16, "vemb.patch_out"); _chk(cls, F32, "vemb.cls"); _chk(pos, F32, "vemb.pos")
     d = patch_out.shape[1]
     x = torch.empty((batch * (npatch + 1), d), dtype=BF16, device=patch_out.device)
-    L.check(L.lib().clipn_vision_embed_fwd(patch_out.data_ptr(), cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch,
+    _call(L.lib().clipn_vision_embed_fwd(patch_out.data_ptr(), cls.data_ptr(), pos.data_ptr(), x.data_ptr(), batch,
                                            npatch, d, _stream()))
     return x
 
@@ -143,7 +162,7 @@ def vision_embed_bwd(dx, dcls, dpos, batch, npatch):
     _chk(dx, BF16, "vembb.dx")
     d = dx.shape[1]
     dpatch = torch.empty((batch * npatch, d), dtype=BF16, device=dx.device)
-    L.check(L.lib().clipn_vision_embed_bwd(dx.data_ptr(), dpatch.data_ptr(), _ptr(dcls), _ptr(dpos), batch, npatch, d,
+    _call(L.lib().clipn_vision_embed_bwd(dx.data_ptr(), dpatch.data_ptr(), _ptr(dcls), _ptr(dpos), batch, npatch, d,
                                            _stream()))
     return dpatch
 
@@ -154,7 +173,7 @@ def text_embed_fwd(ids, table, pos):
     vocab, d = table.shape
     x = torch.empty((B * S, d), dtype=BF16, device=ids.device)
     eot = torch.empty(B, dtype=torch.int32, device=ids.device)
-    L.check(L.lib().clipn_text_embed_fwd(ids.data_ptr(), table.data_ptr(), pos.data_ptr(), x.data_ptr(), eot.data_ptr(),
+    _call(L.lib().clipn_text_embed_fwd(ids.data_ptr(), table.data_ptr(), pos.data_ptr(), x.data_ptr(), eot.data_ptr(),
                                          B, S, d, vocab, _stream()))
     return x, eot
 
@@ -163,7 +182,7 @@ def text_embed_bwd(ids, dx, dtable, dpos):
     _chk(ids, torch.int64, "tembb.ids"); _chk(dx, BF16, "tembb.dx"); _chk(dtable, F32, "tembb.dtable")
     B, S = ids.shape
     vocab, d = dtable.shape
-    L.check(L.lib().clipn_text_embed_bwd(ids.data_ptr(), dx.data_ptr(), dtable.data_ptr(), _ptr(dpos), B, S, d, vocab,
+    _call(L.lib().clipn_text_embed_bwd(ids.data_ptr(), dx.data_ptr(), dtable.data_ptr(), _ptr(dpos), B, S, d, vocab,
                                          _stream()))
 
 
@@ -171,7 +190,7 @@ def gather_rows(x, idx, batch, seq):
     _chk(x, BF16, "gather.x")
     d = x.shape[1]
     out = torch.empty((batch, d), dtype=BF16, device=x.device)
-    L.check(L.lib().clipn_gather_rows(x.data_ptr(), _ptr(idx), out.data_ptr(), batch, seq, d, _stream()))
+    _call(L.lib().clipn_gather_rows(x.data_ptr(), _ptr(idx), out.data_ptr(), batch, seq, d, _stream()))
     return out
 
 
@@ -179,7 +198,7 @@ def scatter_rows(dpooled, idx, batch, seq, out=None):
     _chk(dpooled, BF16, "scatter.dpooled")
     d = dpooled.shape[1]
     dx = out if out is not None else torch.empty((batch * seq, d), dtype=BF16, device=dpooled.device)
-    L.check(L.lib().clipn_scatter_rows(dpooled.data_ptr(), _ptr(idx), dx.data_ptr(), batch, seq, d, _stream()))
+    _call(L.lib().clipn_scatter_rows(dpooled.data_ptr(), _ptr(idx), dx.data_ptr(), batch, seq, d, _stream()))
     return dx
 
 
@@ -188,7 +207,7 @@ def l2norm_fwd(x):
     rows, d = x.shape
     y = torch.empty_like(x)
     inv = torch.empty(rows, dtype=F32, device=x.device)
-    L.check(L.lib().clipn_l2norm_fwd(x.data_ptr(), y.data_ptr(), inv.data_ptr(), rows, d, _stream()))
+    _call(L.lib().clipn_l2norm_fwd(x.data_ptr(), y.data_ptr(), inv.data_ptr(), rows, d, _stream()))
     return y, inv
 
 
@@ -196,7 +215,7 @@ def l2norm_bwd(dy, y, inv):
     assert dy.dtype in (F32, BF16) and dy.is_contiguous() and dy.is_cuda
     rows, d = y.shape
     dx = torch.empty_like(y)
-    L.check(L.lib().clipn_l2norm_bwd(dy.data_ptr(), int(dy.dtype == F32), y.data_ptr(), inv.data_ptr(), dx.data_ptr(),
+    _call(L.lib().clipn_l2norm_bwd(dy.data_ptr(), int(dy.dtype == F32), y.data_ptr(), inv.data_ptr(), dx.data_ptr(),
                                      rows, d, _stream()))
     return dx
 
@@ -204,13 +223,13 @@ def l2norm_bwd(dy, y, inv):
 def colsum(x, out):
     _chk(x, BF16, "colsum.x"); _chk(out, F32, "colsum.out")
     rows, n = x.shape
-    L.check(L.lib().clipn_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), rows, n, _stream()))
+    _call(L.lib().clipn_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), rows, n, _stream()))
 
 
 def cast_f32_to_bf16(x, out=None):
     _chk(x, F32, "cast.x")
     y = out if out is not None else torch.empty(x.shape, dtype=BF16, device=x.device)
-    L.check(L.lib().clipn_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    _call(L.lib().clipn_cast_f32_to_bf16(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
 
@@ -229,7 +248,7 @@ def clip_lse_fwd(rows: torch.Tensor, col_ptrs: Sequence[int], scale: torch.Tenso
     ws = torch.empty(L.lib().clipn_clip_lse_workspace(b, world * b), dtype=F32, device=rows.device)
     lse = torch.empty(b, dtype=F32, device=rows.device)
     pos = torch.zeros(b, dtype=F32, device=rows.device)
-    L.check(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
+    _call(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
                                        label_offset, lse.data_ptr(), pos.data_ptr(), ws.data_ptr(), _stream()))
     return lse, pos
 
@@ -239,7 +258,7 @@ def clip_dlogits(rows, col_ptrs, scale, label_offset, row_lse, col_lse, col_w, g
     b, e = rows.shape
     world = len(col_ptrs)
     out = torch.empty((b, world * b), dtype=BF16, device=rows.device)
-    L.check(L.lib().clipn_clip_dlogits(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
+    _call(L.lib().clipn_clip_dlogits(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
                                        label_offset, row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(),
                                        _ptr(scalar_acc), _stream()))
     return out
@@ -250,7 +269,7 @@ def clip_dfeat(dlogits, col_ptrs, e, alpha: torch.Tensor, out_dtype=BF16):
     b = dlogits.shape[0]
     world = len(col_ptrs)
     out = torch.empty((b, e), dtype=out_dtype, device=dlogits.device)
-    L.check(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, alpha.data_ptr(),
+    _call(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, alpha.data_ptr(),
                                      out.data_ptr(), int(out_dtype == F32), _stream()))
     return out
 
@@ -259,7 +278,7 @@ def siglip_block(img, txt, scale, bias, negative_only, gscale, loss_acc, scalar_
     _chk(img, BF16, "siglip.img"); _chk(txt, BF16, "siglip.txt")
     b, e = img.shape
     dl = torch.empty((b, b), dtype=BF16, device=img.device) if want_grad else None
-    L.check(L.lib().clipn_siglip_block(img.data_ptr(), txt.data_ptr(), b, e, scale.data_ptr(), bias.data_ptr(),
+    _call(L.lib().clipn_siglip_block(img.data_ptr(), txt.data_ptr(), b, e, scale.data_ptr(), bias.data_ptr(),
                                        int(negative_only), gscale, loss_acc.data_ptr(), _ptr(dl), _ptr(scalar_acc),
                                        _stream()))
     return dl

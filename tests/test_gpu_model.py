@@ -84,12 +84,26 @@ def test_vitb32_forward_loss_and_grad_probes_vs_reference_fixture(golden_dir):
     out, loss = _run_native(m, image, text)
     _check_features(out, gold["fp32"])
     assert abs(float(loss) - gold["fp32"]["loss"]) <= 1e-2
-    worst = 0.0
+    # Gradient fingerprints (L2 norm, projection on a seeded random direction) of all 302 parameters vs the fp32
+    # reference.  Noise floor = the reference's OWN --precision bf16 run vs its fp32 run, both in the fixture:
+    # norm deviation median 0.14 % / max 1.1 %; projection deviation (in units of ||g||) median 2.1 %, p90 5.4 %,
+    # max 11.5 %.  We require every statistic within 1.5x of that floor.
+    params = dict(m.named_parameters())
+    dn, dp, fn, fp = [], [], [], []
     for k, pr in gold["fp32"]["grad_probes"].items():
-        mine = _probe(k, dict(m.named_parameters())[k].grad)
-        worst = max(worst, float(abs(mine[0] - pr[0]) / (pr[0].abs() + 1e-9)))
-        assert abs(mine[0] - pr[0]) <= 5e-2 * pr[0].abs() + 1e-7, (k, mine, pr)
-        assert abs(mine[1] - pr[1]) <= 8e-2 * pr[0].abs() + 1e-7, (k, mine, pr)
+        mine = _probe(k, params[k].grad)
+        rb = gold["bf16"]["grad_probes"][k]
+        dn.append(float(abs(mine[0] - pr[0]) / (pr[0].abs() + 1e-12)))
+        dp.append(float(abs(mine[1] - pr[1]) / (pr[0].abs() + 1e-12)))
+        fn.append(float(abs(rb[0] - pr[0]) / (pr[0].abs() + 1e-12)))
+        fp.append(float(abs(rb[1] - pr[1]) / (pr[0].abs() + 1e-12)))
+    t = lambda v: torch.tensor(v)
+    stats = lambda v: (float(t(v).median()), float(t(v).quantile(0.9)), float(t(v).max()))
+    mine_n, mine_p, ref_n, ref_p = stats(dn), stats(dp), stats(fn), stats(fp)
+    print("grad norm dev (median,p90,max): ours", mine_n, "reference bf16", ref_n)
+    print("grad proj dev (median,p90,max): ours", mine_p, "reference bf16", ref_p)
+    for a, b in zip(mine_n + mine_p, ref_n + ref_p):
+        assert a <= 1.5 * b + 2e-3, (mine_n, mine_p, ref_n, ref_p)
 
 
 def test_state_dict_names_shapes_dtypes_match_reference_contract():
