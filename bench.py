@@ -86,26 +86,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores() -> int:
+    """Host threads this process may really use: affinity mask and cgroup CPU quota, not the machine's core count."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 # ------------------------------------------------------------------------------------------- CPU reference arm
 def run_cpu_reference(steps: int, warmup: int, batch: int = 32):
     """The reference's own CPU train step (config[0]: ViT-B-32 fp32, batch 32, all host threads), restated by the
     oracle port (oracle/clip_oracle.CpuTrainer: reference CLIPTask + train_step + AdamW + clamp)."""
     import torch
     from oracle import clip_oracle as O
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cfg = O.CONFIGS["ViT-B-32"]
     tr = O.CpuTrainer(cfg, seed=0)
     image, text = O.synthetic_batch(cfg, batch, seed=0)
-    for _ in range(warmup):
+    budget_s = float(os.environ.get("CLIPN_CPU_BASELINE_BUDGET_S", "40"))  # bounded sample: whole leg < ~1 min
+    t_begin = time.perf_counter()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
         tr.step(image, text)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        tr.step(image, text)
-    dt = (time.perf_counter() - t0) / max(steps, 1)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    timed = times[min(warmup, len(times) - 1):]
+    dt = sum(timed) / len(timed)
     return {"value": batch / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-            "sample": f"ViT-B-32 fp32 CPU train step, batch {batch}, {steps} timed steps after {warmup} warm-up "
-                      f"(oracle port of reference CLIPTask+train_step+AdamW)", "ms_per_step": dt * 1e3}
+            "sample": f"ViT-B-32 fp32 CPU train step, batch {batch}, {len(timed)} timed steps after "
+                      f"{len(times) - len(timed)} warm-up, {cores} threads (oracle port of reference "
+                      f"CLIPTask+train_step+AdamW)", "ms_per_step": dt * 1e3}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm

@@ -1,19 +1,22 @@
 // Attention core for the CLIP towers (F.scaled_dot_product_attention, transformer.py:223-228), head_dim 64.
 //
-// Sequences are short (50 / 77 / 197 tokens) so one CTA owns one (batch, head): Q, K, V (and dO in the
-// backward) live in shared memory for the whole CTA, each warp owns 16-row tiles, S = QK^T and PV run on
-// tensor cores (mma.sync m16n8k16 bf16 -> fp32; the tiles are far below the 128-row tcgen05 atom and the
-// op is 1.6 % of the step's FLOPs — it is HBM-bound), softmax is a warp-shuffle (quad)
-// reduction in registers with online rescaling, the causal mask is a predicate (no mask tensor).
-// Backward recomputes P from the saved log-sum-exp; pass A (warp = 16 queries) produces dQ, pass B
-// (warp = 16 keys, transposed tiles) produces dK and dV, so there are no atomics and the result is
-// deterministic.
+// Sequences are short (50 / 77 / 197 tokens) and the op is 1.6 % of the step's FLOPs: it is HBM-bound, so the
+// design goal is bytes in flight, not tensor throughput.  Persistent CTAs loop over (batch, head) work items with
+// a 2-stage cp.async pipeline: while the warps compute item i out of shared memory, the 16-byte cp.async copies
+// of item i+1 (Q, K, V and, in the backward, dO) are already in flight.  Inside an item every warp owns 16-row
+// tiles; S = QK^T and PV run on tensor cores (mma.sync m16n8k16 bf16 -> fp32 — the tiles are 16x64, far below the
+// 128-row tcgen05 atom), softmax is a warp-shuffle (quad) reduction in registers with online rescaling, the
+// causal mask is a predicate (no mask tensor).  Outputs are staged through shared memory and leave as full
+// 128-byte rows.
+// Backward recomputes P from the saved log-sum-exp and uses D_i = sum_j P_ij dP_ij (== rowsum(dO o O)), so the
+// forward output is never re-read: phase 1 (warp = 16 queries) computes D, phase 2a dQ, phase 2b (warp = 16 keys,
+// transposed tiles) dK and dV — no atomics, deterministic.
 #include "common.cuh"
 
 namespace clipn {
 
-constexpr int HD = 64;       // head dim
-constexpr int LDS = 72;      // padded smem row (bf16 elements): 144 B => conflict-free fragment loads
+constexpr int HD = 64;   // head dim
+constexpr int LDS = 72;  // padded smem row (bf16 elements): 144 B => conflict-free fragment loads
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -29,6 +32,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(smem_row)));
 }
 __device__ __forceinline__ uint32_t lds32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
 // A-operand fragments (16 rows x 64 k) of a row-major smem tile starting at row r0.
 __device__ __forceinline__ void load_a_frags(const __nv_bfloat16* tile, int r0, int lane, uint32_t (&a)[4][4]) {
@@ -48,7 +59,7 @@ __device__ __forceinline__ void mma_a_tT(float (&acc)[4], const uint32_t (&a)[4]
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) mma_bf16(acc, a[kk], lds32(row + kk * 16), lds32(row + kk * 16 + 8));
 }
-// For a 16-deep k-slab starting at smem row k0 of T (row-major [k][64]): out[jn] += Pa(16x16) * T[k0..k0+15][jn*8..]
+// out[jn] (16 x 64) += Pa(16x16) * T[k0..k0+15][0..63]   (T row-major [k][64]; B fragments via ldmatrix.trans)
 __device__ __forceinline__ void mma_p_t(float (&out)[8][4], const uint32_t (&pa)[4], const __nv_bfloat16* T, int k0,
                                         int lane) {
   const int mi = lane >> 3, ri = lane & 7;
@@ -60,308 +71,352 @@ __device__ __forceinline__ void mma_p_t(float (&out)[8][4], const uint32_t (&pa)
     mma_bf16(out[jn + 1], pa, b[2], b[3]);
   }
 }
+__device__ __forceinline__ void pack_frag(uint32_t (&pa)[4], const float (&t0)[4], const float (&t1)[4]) {
+  pa[0] = pack_bf16x2(t0[0], t0[1]);
+  pa[1] = pack_bf16x2(t0[2], t0[3]);
+  pa[2] = pack_bf16x2(t1[0], t1[1]);
+  pa[3] = pack_bf16x2(t1[2], t1[3]);
+}
 
-__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t src_ld, int rows,
-                                          int rows_pad) {
-  for (int i = threadIdx.x; i < rows_pad * 8; i += blockDim.x) {
+// async copy of `rows` x 64 bf16 (128 B per row) into a padded smem tile
+__device__ __forceinline__ void tile_cp_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t src_ld, int rows) {
+  for (int i = threadIdx.x; i < rows * 8; i += blockDim.x) {
     const int r = i >> 3, v = i & 7;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (r < rows) val = *reinterpret_cast<const uint4*>(src + r * src_ld + v * 8);
-    *reinterpret_cast<uint4*>(dst + r * LDS + v * 8) = val;
+    cp_async16(dst + r * LDS + v * 8, src + r * src_ld + v * 8);
+  }
+}
+__device__ __forceinline__ void tile_zero_pad(__nv_bfloat16* dst, int rows, int rows_pad) {
+  for (int i = threadIdx.x; i < (rows_pad - rows) * 8; i += blockDim.x) {
+    const int r = rows + (i >> 3), v = i & 7;
+    *reinterpret_cast<uint4*>(dst + r * LDS + v * 8) = make_uint4(0, 0, 0, 0);
+  }
+}
+// write a warp's staged 16 x 64 bf16 tile (rows r0.. of `stage`, LDS pitch) to global rows as 128-byte segments
+__device__ __forceinline__ void store_tile16(const __nv_bfloat16* stage, __nv_bfloat16* gdst, int64_t g_ld, int r0,
+                                             int seq, int lane) {
+  for (int i = lane; i < 16 * 8; i += 32) {
+    const int r = i >> 3, v = i & 7;
+    if (r0 + r < seq)
+      *reinterpret_cast<uint4*>(gdst + static_cast<int64_t>(r0 + r) * g_ld + v * 8) =
+          *reinterpret_cast<const uint4*>(stage + r * LDS + v * 8);
+  }
+}
+__device__ __forceinline__ void stage_frag_tile(__nv_bfloat16* stage, const float (&o)[8][4], float s0, float s1,
+                                                int lane) {
+  const int r = lane >> 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = j * 8 + (lane & 3) * 2;
+    *reinterpret_cast<uint32_t*>(stage + r * LDS + c) = pack_bf16x2(o[j][0] * s0, o[j][1] * s0);
+    *reinterpret_cast<uint32_t*>(stage + (r + 8) * LDS + c) = pack_bf16x2(o[j][2] * s1, o[j][3] * s1);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ lse_out,
-                                                            int seq, int heads, int causal, float scale) {
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, (MAXW <= 5) ? 3 : 2)
+attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                     float* __restrict__ lse_out, int items, int seq, int heads, int causal, float scale) {
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Lp = (seq + 15) & ~15;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
-  __nv_bfloat16* sK = sQ + Lp * LDS;
-  __nv_bfloat16* sV = sK + Lp * LDS;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int stage_elems = 3 * Lp * LDS;
+  __nv_bfloat16* sbase = reinterpret_cast<__nv_bfloat16*>(smem_att);
   const int d = heads * HD;
   const int64_t ld = 3 * static_cast<int64_t>(d);
-  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
-  load_tile(sQ, base, ld, seq, Lp);
-  load_tile(sK, base + d, ld, seq, Lp);
-  load_tile(sV, base + 2 * d, ld, seq, Lp);
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float sl2 = scale * kLog2e;
-  for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
-    uint32_t qa[4][4];
-    load_a_frags(sQ, r0, lane, qa);
-    float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
-    float o[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
-    const int row_a = r0 + (lane >> 2);
-    int kv_end = seq;
-    if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
-    for (int kc = 0; kc < kv_end; kc += 64) {
-      float s[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
-        if (kc + j * 8 < kv_end) mma_a_tT(s[j], qa, sK, kc + j * 8, lane);
-      }
-      float cmax[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = kc + j * 8 + (lane & 3) * 2 + (e & 1);
-          const int row = row_a + (e >> 1) * 8;
-          const bool ok = key < kv_end && key < seq && !(causal && key > row);
-          s[j][e] = ok ? s[j][e] * sl2 : -INFINITY;
-          cmax[e >> 1] = fmaxf(cmax[e >> 1], s[j][e]);
-        }
-      float corr[2], mref[2];
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 1));
-        cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 2));
-        const float mn = fmaxf(m_i[t], cmax[t]);
-        mref[t] = (mn == -INFINITY) ? 0.f : mn;
-        corr[t] = exp2f(m_i[t] - mref[t]);  // m_i = -inf -> 0
-        m_i[t] = mn;
-        l_i[t] *= corr[t];
-      }
+
+  for (int s = 0; s < 2; ++s)
+    for (int t = 0; t < 3; ++t) tile_zero_pad(sbase + s * stage_elems + t * Lp * LDS, seq, Lp);
+
+  auto prefetch = [&](int item, int s) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    __nv_bfloat16* st = sbase + s * stage_elems;
+    tile_cp_async(st, base, ld, seq);
+    tile_cp_async(st + Lp * LDS, base + d, ld, seq);
+    tile_cp_async(st + 2 * Lp * LDS, base + 2 * d, ld, seq);
+  };
+
+  int item = blockIdx.x;
+  if (item < items) prefetch(item, 0);
+  cp_async_commit();
+  for (int it = 0; item < items; item += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int next = item + gridDim.x;
+    if (next < items) prefetch(next, s ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    __nv_bfloat16* sQ = sbase + s * stage_elems;
+    const __nv_bfloat16* sK = sQ + Lp * LDS;
+    const __nv_bfloat16* sV = sK + Lp * LDS;
+    const int b = item / heads, h = item % heads;
+
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      uint32_t qa[4][4];
+      load_a_frags(sQ, r0, lane, qa);
+      float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+      float o[8][4];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          o[j][e] *= corr[e >> 1];
-          s[j][e] = exp2f(s[j][e] - mref[e >> 1]);
-          l_i[e >> 1] += s[j][e];
+        for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+      const int row_a = r0 + (lane >> 2);
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      for (int kc = 0; kc < kv_end; kc += 64) {
+        float sc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+          if (kc + j * 8 < kv_end) mma_a_tT(sc[j], qa, sK, kc + j * 8, lane);
+        }
+        float cmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kc + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int row = row_a + (e >> 1) * 8;
+            const bool ok = key < kv_end && !(causal && key > row);
+            sc[j][e] = ok ? sc[j][e] * sl2 : -INFINITY;
+            cmax[e >> 1] = fmaxf(cmax[e >> 1], sc[j][e]);
+          }
+        float corr[2], mref[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 1));
+          cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 2));
+          const float mn = fmaxf(m_i[t], cmax[t]);
+          mref[t] = (mn == -INFINITY) ? 0.f : mn;
+          corr[t] = exp2f(m_i[t] - mref[t]);  // m_i = -inf -> 0
+          m_i[t] = mn;
+          l_i[t] *= corr[t];
         }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kc + kk * 16 < kv_end) {
-          uint32_t pa[4];
-          pa[0] = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
-          pa[1] = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-          pa[2] = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-          pa[3] = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-          mma_p_t(o, pa, sV, kc + kk * 16, lane);
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[j][e] *= corr[e >> 1];
+            sc[j][e] = exp2f(sc[j][e] - mref[e >> 1]);
+            l_i[e >> 1] += sc[j][e];
+          }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kc + kk * 16 < kv_end) {
+            uint32_t pa[4];
+            pack_frag(pa, sc[2 * kk], sc[2 * kk + 1]);
+            mma_p_t(o, pa, sV, kc + kk * 16, lane);
+          }
         }
       }
-    }
-    float inv[2];
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-      l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 1);
-      l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 2);
-      inv[t] = l_i[t] > 0.f ? 1.f / l_i[t] : 0.f;
-    }
-    // stage the 16x64 output tile in this warp's (now dead) Q rows, then write coalesced 128-byte rows
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = j * 8 + (lane & 3) * 2;
-      *reinterpret_cast<uint32_t*>(sQ + row_a * LDS + c) = pack_bf16x2(o[j][0] * inv[0], o[j][1] * inv[0]);
-      *reinterpret_cast<uint32_t*>(sQ + (row_a + 8) * LDS + c) = pack_bf16x2(o[j][2] * inv[1], o[j][3] * inv[1]);
-    }
-    __syncwarp();
-    for (int i = lane; i < 16 * 8; i += 32) {
-      const int r = r0 + (i >> 3), v = i & 7;
-      if (r < seq)
-        *reinterpret_cast<uint4*>(out + (static_cast<int64_t>(b) * seq + r) * d + h * HD + v * 8) =
-            *reinterpret_cast<const uint4*>(sQ + r * LDS + v * 8);
-    }
-    if ((lane & 3) == 0 && lse_out != nullptr) {
+      float inv[2];
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
-        const int r = row_a + t * 8;
-        if (r < seq)
-          lse_out[(static_cast<int64_t>(b) * heads + h) * seq + r] = (m_i[t] + log2f(l_i[t])) * kLn2;
+        l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 1);
+        l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 2);
+        inv[t] = l_i[t] > 0.f ? 1.f / l_i[t] : 0.f;
+      }
+      // stage the 16x64 output tile in this warp's (now dead) Q rows, then write coalesced 128-byte rows
+      __syncwarp();
+      stage_frag_tile(sQ + r0 * LDS, o, inv[0], inv[1], lane);
+      __syncwarp();
+      store_tile16(sQ + r0 * LDS, out + static_cast<int64_t>(b) * seq * d + h * HD, d, r0, seq, lane);
+      if ((lane & 3) == 0 && lse_out != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int r = row_a + t * 8;
+          if (r < seq) lse_out[(static_cast<int64_t>(b) * heads + h) * seq + r] = (m_i[t] + log2f(l_i[t])) * kLn2;
+        }
       }
     }
+    __syncthreads();  // stage s is re-filled by the prefetch issued at the top of the next iteration
   }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                            const __nv_bfloat16* __restrict__ out,
-                                                            const __nv_bfloat16* __restrict__ dout,
-                                                            const float* __restrict__ lse_in,
-                                                            __nv_bfloat16* __restrict__ dqkv, int seq, int heads,
-                                                            int causal, float scale) {
+template <int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 2)
+attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                     const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, int items, int seq, int heads,
+                     int causal, float scale) {
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Lp = (seq + 15) & ~15;
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
-  __nv_bfloat16* sK = sQ + Lp * LDS;
-  __nv_bfloat16* sV = sK + Lp * LDS;
-  __nv_bfloat16* sDO = sV + Lp * LDS;
-  float* sLse = reinterpret_cast<float*>(sDO + Lp * LDS);  // log2-domain LSE
+  const int stage_elems = 4 * Lp * LDS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __nv_bfloat16* sbase = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sOut = sbase + 2 * stage_elems + warp * 16 * LDS;  // per-warp output staging tile
+  float* sLse = reinterpret_cast<float*>(sbase + 2 * stage_elems + nwarps * 16 * LDS);  // log2-domain LSE
   float* sD = sLse + Lp;
-  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int d = heads * HD;
   const int64_t ld = 3 * static_cast<int64_t>(d);
-  const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
-  const __nv_bfloat16* obase = out + static_cast<int64_t>(b) * seq * d + h * HD;
-  const __nv_bfloat16* dobase = dout + static_cast<int64_t>(b) * seq * d + h * HD;
-  load_tile(sQ, base, ld, seq, Lp);
-  load_tile(sK, base + d, ld, seq, Lp);
-  load_tile(sV, base + 2 * d, ld, seq, Lp);
-  load_tile(sDO, dobase, d, seq, Lp);
-  for (int i = threadIdx.x; i < Lp; i += blockDim.x)
-    sLse[i] = (i < seq) ? lse_in[(static_cast<int64_t>(b) * heads + h) * seq + i] * kLog2e : 0.f;
-  __syncthreads();
-  // D[r] = sum_c dO[r,c] * O[r,c]  (8 lanes per row)
-  for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {
-    const int r = i >> 3, v = i & 7;
-    float acc = 0.f;
-    if (r < seq) {
-      float a[8], c[8];
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(r) * d + v * 8), a);
-      unpack_bf16x8(*reinterpret_cast<const uint4*>(sDO + r * LDS + v * 8), c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc += a[j] * c[j];
-    }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    if (v == 0) sD[r] = acc;
-  }
-  __syncthreads();
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float sl2 = scale * kLog2e;
-  __nv_bfloat16* dq_base = dqkv + static_cast<int64_t>(b) * seq * ld + h * HD;
 
-  // ---------------- pass A: warp owns 16 queries -> dQ ----------------
-  for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
-    uint32_t qa[4][4], doa[4][4];
-    load_a_frags(sQ, r0, lane, qa);
-    load_a_frags(sDO, r0, lane, doa);
-    const int row_a = r0 + (lane >> 2);
-    const float lse_r[2] = {sLse[row_a], sLse[row_a + 8]};
-    const float d_r[2] = {sD[row_a], sD[row_a + 8]};
-    float dq[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
-    int kv_end = seq;
-    if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
-    for (int kc = 0; kc < kv_end; kc += 64) {
-      float ds[8][4];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        if (kc + j * 8 < kv_end) {
-          mma_a_tT(s, qa, sK, kc + j * 8, lane);
-          mma_a_tT(dp, doa, sV, kc + j * 8, lane);
-        }
+  for (int s = 0; s < 2; ++s)
+    for (int t = 0; t < 4; ++t) tile_zero_pad(sbase + s * stage_elems + t * Lp * LDS, seq, Lp);
+
+  auto prefetch = [&](int item, int s) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    __nv_bfloat16* st = sbase + s * stage_elems;
+    tile_cp_async(st, base, ld, seq);
+    tile_cp_async(st + Lp * LDS, base + d, ld, seq);
+    tile_cp_async(st + 2 * Lp * LDS, base + 2 * d, ld, seq);
+    tile_cp_async(st + 3 * Lp * LDS, dout + static_cast<int64_t>(b) * seq * d + h * HD, d, seq);
+  };
+
+  int item = blockIdx.x;
+  if (item < items) prefetch(item, 0);
+  cp_async_commit();
+  for (int it = 0; item < items; item += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int next = item + gridDim.x;
+    if (next < items) prefetch(next, s ^ 1);
+    cp_async_commit();
+    const int b = item / heads, h = item % heads;
+    for (int i = threadIdx.x; i < Lp; i += blockDim.x)
+      sLse[i] = (i < seq) ? lse_in[(static_cast<int64_t>(b) * heads + h) * seq + i] * kLog2e : 0.f;
+    cp_async_wait<1>();
+    __syncthreads();
+    const __nv_bfloat16* sQ = sbase + s * stage_elems;
+    const __nv_bfloat16* sK = sQ + Lp * LDS;
+    const __nv_bfloat16* sV = sK + Lp * LDS;
+    const __nv_bfloat16* sDO = sV + Lp * LDS;
+    __nv_bfloat16* dq_base = dqkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+
+    // ---------------- phase 1: D[i] = sum_j P_ij * dP_ij  (warp owns 16 queries) ----------------
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      uint32_t qa[4][4], doa[4][4];
+      load_a_frags(sQ, r0, lane, qa);
+      load_a_frags(sDO, r0, lane, doa);
+      const int row_a = r0 + (lane >> 2);
+      const float lse_r[2] = {sLse[row_a], sLse[row_a + 8]};
+      float dsum[2] = {0.f, 0.f};
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      for (int k0 = 0; k0 < kv_end; k0 += 8) {
+        float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_a_tT(sc, qa, sK, k0, lane);
+        mma_a_tT(dp, doa, sV, k0, lane);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int key = kc + j * 8 + (lane & 3) * 2 + (e & 1);
+          const int key = k0 + (lane & 3) * 2 + (e & 1);
           const int row = row_a + (e >> 1) * 8;
-          const bool ok = key < kv_end && key < seq && row < seq && !(causal && key > row);
-          const float p = ok ? exp2f(s[e] * sl2 - lse_r[e >> 1]) : 0.f;
-          ds[j][e] = p * (dp[e] - d_r[e >> 1]);
+          const bool ok = key < kv_end && row < seq && !(causal && key > row);
+          if (ok) dsum[e >> 1] += exp2f(sc[e] * sl2 - lse_r[e >> 1]) * dp[e];
         }
       }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (kc + kk * 16 < kv_end) {
-          uint32_t pa[4];
-          pa[0] = pack_bf16x2(ds[2 * kk][0], ds[2 * kk][1]);
-          pa[1] = pack_bf16x2(ds[2 * kk][2], ds[2 * kk][3]);
-          pa[2] = pack_bf16x2(ds[2 * kk + 1][0], ds[2 * kk + 1][1]);
-          pa[3] = pack_bf16x2(ds[2 * kk + 1][2], ds[2 * kk + 1][3]);
-          mma_p_t(dq, pa, sK, kc + kk * 16, lane);
-        }
+      for (int t = 0; t < 2; ++t) {
+        dsum[t] += __shfl_xor_sync(0xffffffffu, dsum[t], 1);
+        dsum[t] += __shfl_xor_sync(0xffffffffu, dsum[t], 2);
+      }
+      if ((lane & 3) == 0) {
+        sD[row_a] = dsum[0];
+        sD[row_a + 8] = dsum[1];
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = j * 8 + (lane & 3) * 2;
-      if (row_a < seq)
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(row_a) * ld + c) =
-            pack_bf16x2(dq[j][0] * scale, dq[j][1] * scale);
-      if (row_a + 8 < seq)
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(row_a + 8) * ld + c) =
-            pack_bf16x2(dq[j][2] * scale, dq[j][3] * scale);
-    }
-  }
+    __syncthreads();
 
-  // ---------------- pass B: warp owns 16 keys -> dK, dV (transposed tiles) ----------------
-  for (int c0 = warp * 16; c0 < Lp; c0 += nwarps * 16) {
-    uint32_t ka[4][4], va[4][4];
-    load_a_frags(sK, c0, lane, ka);
-    load_a_frags(sV, c0, lane, va);
-    const int key_a = c0 + (lane >> 2);
-    float dk[8][4], dv[8][4];
+    // ---------------- phase 2a: warp owns 16 queries -> dQ ----------------
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      uint32_t qa[4][4], doa[4][4];
+      load_a_frags(sQ, r0, lane, qa);
+      load_a_frags(sDO, r0, lane, doa);
+      const int row_a = r0 + (lane >> 2);
+      const float lse_r[2] = {sLse[row_a], sLse[row_a + 8]};
+      const float d_r[2] = {sD[row_a], sD[row_a + 8]};
+      float dq[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) dk[j][e] = dv[j][e] = 0.f;
-    const int q_begin = causal ? (c0 & ~63) : 0;  // queries < c0 never see these keys
-    for (int qc = q_begin; qc < seq; qc += 64) {
-      float pt[8][4], dst[8][4];
+        for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      for (int k0 = 0; k0 < kv_end; k0 += 16) {
+        float ds[2][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool live = (qc + j * 8 < seq) && !(causal && qc + j * 8 + 7 < c0);
-        if (live) {
-          mma_a_tT(s, ka, sQ, qc + j * 8, lane);
-          mma_a_tT(dp, va, sDO, qc + j * 8, lane);
+        for (int t = 0; t < 2; ++t) {
+          float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          if (k0 + t * 8 < kv_end) {
+            mma_a_tT(sc, qa, sK, k0 + t * 8, lane);
+            mma_a_tT(dp, doa, sV, k0 + t * 8, lane);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + t * 8 + (lane & 3) * 2 + (e & 1);
+            const int row = row_a + (e >> 1) * 8;
+            const bool ok = key < kv_end && row < seq && !(causal && key > row);
+            ds[t][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
+          }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int qi = qc + j * 8 + (lane & 3) * 2 + (e & 1);
-          const int key = key_a + (e >> 1) * 8;
-          const bool ok = live && qi < seq && key < seq && !(causal && key > qi);
-          const float p = ok ? exp2f(s[e] * sl2 - sLse[qi < Lp ? qi : 0]) : 0.f;
-          pt[j][e] = p;
-          dst[j][e] = ok ? p * (dp[e] - sD[qi]) : 0.f;
-        }
+        uint32_t pa[4];
+        pack_frag(pa, ds[0], ds[1]);
+        mma_p_t(dq, pa, sK, k0, lane);
       }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (qc + kk * 16 < seq) {
-          uint32_t pa[4], da[4];
-          pa[0] = pack_bf16x2(pt[2 * kk][0], pt[2 * kk][1]);
-          pa[1] = pack_bf16x2(pt[2 * kk][2], pt[2 * kk][3]);
-          pa[2] = pack_bf16x2(pt[2 * kk + 1][0], pt[2 * kk + 1][1]);
-          pa[3] = pack_bf16x2(pt[2 * kk + 1][2], pt[2 * kk + 1][3]);
-          da[0] = pack_bf16x2(dst[2 * kk][0], dst[2 * kk][1]);
-          da[1] = pack_bf16x2(dst[2 * kk][2], dst[2 * kk][3]);
-          da[2] = pack_bf16x2(dst[2 * kk + 1][0], dst[2 * kk + 1][1]);
-          da[3] = pack_bf16x2(dst[2 * kk + 1][2], dst[2 * kk + 1][3]);
-          mma_p_t(dv, pa, sDO, qc + kk * 16, lane);
-          mma_p_t(dk, da, sQ, qc + kk * 16, lane);
-        }
-      }
+      __syncwarp();
+      stage_frag_tile(sOut, dq, scale, scale, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base, ld, r0, seq, lane);
     }
+
+    // ---------------- phase 2b: warp owns 16 keys -> dK, dV (transposed tiles) ----------------
+    for (int c0 = warp * 16; c0 < Lp; c0 += nwarps * 16) {
+      uint32_t ka[4][4], va[4][4];
+      load_a_frags(sK, c0, lane, ka);
+      load_a_frags(sV, c0, lane, va);
+      const int key_a = c0 + (lane >> 2);
+      float dk[8][4], dv[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = j * 8 + (lane & 3) * 2;
-      if (key_a < seq) {
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(key_a) * ld + d + c) =
-            pack_bf16x2(dk[j][0] * scale, dk[j][1] * scale);
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(key_a) * ld + 2 * d + c) = pack_bf16x2(dv[j][0], dv[j][1]);
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[j][e] = dv[j][e] = 0.f;
+      const int q_begin = causal ? c0 : 0;  // queries < c0 never see these keys (c0 is a multiple of 16)
+      for (int q0 = q_begin; q0 < seq; q0 += 16) {
+        float pt[2][4], dst[2][4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          const bool live = q0 + t * 8 < seq;
+          if (live) {
+            mma_a_tT(sc, ka, sQ, q0 + t * 8, lane);
+            mma_a_tT(dp, va, sDO, q0 + t * 8, lane);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qi = q0 + t * 8 + (lane & 3) * 2 + (e & 1);
+            const int key = key_a + (e >> 1) * 8;
+            const bool ok = live && qi < seq && key < seq && !(causal && key > qi);
+            const float p = ok ? exp2f(sc[e] * sl2 - sLse[qi]) : 0.f;
+            pt[t][e] = p;
+            dst[t][e] = ok ? p * (dp[e] - sD[qi]) : 0.f;
+          }
+        }
+        uint32_t pa[4], da[4];
+        pack_frag(pa, pt[0], pt[1]);
+        pack_frag(da, dst[0], dst[1]);
+        mma_p_t(dv, pa, sDO, q0, lane);
+        mma_p_t(dk, da, sQ, q0, lane);
       }
-      if (key_a + 8 < seq) {
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(key_a + 8) * ld + d + c) =
-            pack_bf16x2(dk[j][2] * scale, dk[j][3] * scale);
-        *reinterpret_cast<uint32_t*>(dq_base + static_cast<int64_t>(key_a + 8) * ld + 2 * d + c) =
-            pack_bf16x2(dv[j][2], dv[j][3]);
-      }
+      __syncwarp();
+      stage_frag_tile(sOut, dk, scale, scale, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base + d, ld, c0, seq, lane);
+      __syncwarp();
+      stage_frag_tile(sOut, dv, 1.f, 1.f, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base + 2 * d, ld, c0, seq, lane);
     }
+    __syncthreads();  // everyone is done with stage s, sLse and sD before they are overwritten
   }
+  cp_async_wait<0>();
 }
 
 static int pick_warps(int seq) {
@@ -379,11 +434,28 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_fwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
   const int Lp = (seq + 15) & ~15;
-  const size_t smem = static_cast<size_t>(3) * Lp * LDS * 2;
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_fwd: sequence too long for the single-CTA kernel (L <= 512)");
-  CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  attention_fwd_kernel<<<batch * heads, pick_warps(seq) * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, seq, heads, causal, scale);
+  const size_t smem = static_cast<size_t>(2) * 3 * Lp * LDS * 2;
+  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_fwd: sequence too long for the in-smem kernel (L <= 256)");
+  const int items = batch * heads;
+  const int nw = pick_warps(seq);
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  const int cap = nw <= 5 ? 3 : 2;
+  if (per_sm > cap) per_sm = cap;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > items) grid = items;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (nw <= 5) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_fwd_kernel<5><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, items, seq, heads,
+                                                         causal, scale);
+  } else {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_fwd_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                         reinterpret_cast<__nv_bfloat16*>(out), lse, items, seq, heads,
+                                                         causal, scale);
+  }
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }
@@ -391,16 +463,35 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
 extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                    int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
                                    clipn_stream_t stream) {
-  CLIPN_REQUIRE(qkv && out && dout && lse && dqkv, "attention_bwd: null pointer");
+  (void)out;  // D = rowsum(dO o O) is recomputed as sum_j P_ij dP_ij: the forward output is not re-read
+  CLIPN_REQUIRE(qkv && dout && lse && dqkv, "attention_bwd: null pointer");
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_bwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
   const int Lp = (seq + 15) & ~15;
-  const size_t smem = static_cast<size_t>(4) * Lp * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_bwd: sequence too long for the single-CTA kernel (L <= 384)");
-  CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  attention_bwd_kernel<<<batch * heads, pick_warps(seq) * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
-      reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), seq, heads, causal, scale);
+  const int nw = pick_warps(seq);
+  const size_t smem = static_cast<size_t>(2) * 4 * Lp * LDS * 2 + static_cast<size_t>(nw) * 16 * LDS * 2 +
+                      static_cast<size_t>(2) * Lp * sizeof(float);
+  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_bwd: sequence too long for the in-smem kernel (L <= 192)");
+  const int items = batch * heads;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > items) grid = items;
+  auto st = static_cast<cudaStream_t>(stream);
+  if (nw <= 5) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_bwd_kernel<5><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                         reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                                         reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads, causal,
+                                                         scale);
+  } else {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_bwd_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                         reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                                         reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads, causal,
+                                                         scale);
+  }
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }

@@ -117,7 +117,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
 }
 __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* smem_src, int c_inner,
                                                   int c_outer) {
-  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(tm)),
                "r"(smem_u32(smem_src)), "r"(c_inner), "r"(c_outer)
                : "memory");

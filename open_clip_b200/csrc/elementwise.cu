@@ -5,7 +5,16 @@
 
 namespace clipn {
 
-constexpr int kMaxChunks = 4;  // a lane holds up to 4 x 8 bf16 of a row  => d <= 1024
+// Row kernels are templated on NCH = 16-byte chunks per lane (a lane holds NCH x 8 bf16 of a row): d <= 256*NCH.
+// Dispatching on NCH keeps the per-lane register arrays exactly as large as the row needs (occupancy).
+#define CLIPN_DISPATCH_NCH(d, CALL)          \
+  do {                                       \
+    const int nch_ = ((d) / 8 + 31) / 32;    \
+    if (nch_ <= 1) { CALL(1); }              \
+    else if (nch_ == 2) { CALL(2); }         \
+    else if (nch_ == 3) { CALL(3); }         \
+    else { CALL(4); }                        \
+  } while (0)
 
 static inline int grid_for_rows(int64_t rows, int rows_per_block) {
   int64_t blocks = (rows + rows_per_block - 1) / rows_per_block;
@@ -16,7 +25,8 @@ static inline int grid_for_rows(int64_t rows, int rows_per_block) {
 // ------------------------------------------------------------------------------------------------
 // LayerNorm forward: y = (x-mean)*rstd*gamma + beta    (layers.py:11-26)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 2) ? 4 : 3) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta,
                                                             __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
@@ -27,10 +37,10 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-    float v[kMaxChunks][8];
+    float v[NCH][8];
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         unpack_bf16x8(xr[ci], v[c]);
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     const float mean = warp_sum(s) / d;
     float sq = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
 #pragma unroll
@@ -54,7 +64,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
     const float rstd = rsqrtf(warp_sum(sq) / d + eps);
     uint4* yr = reinterpret_cast<uint4*>(y + row * d);
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         const float4 g0 = reinterpret_cast<const float4*>(gamma)[ci * 2], g1 = reinterpret_cast<const float4*>(gamma)[ci * 2 + 1];
@@ -78,7 +88,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const __nv_bfloat16*
 // LayerNorm backward.  dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += sum dy*xhat,
 // dbeta += sum dy.  Optional residual-gradient add fused into the store.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+template <int NCH>
+__global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                             const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in,
@@ -94,9 +105,9 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nchunk = d >> 3;
-  float acc_dg[kMaxChunks][8], acc_db[kMaxChunks][8];
+  float acc_dg[NCH][8], acc_db[NCH][8];
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c)
+  for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_dg[c][j] = acc_db[c][j] = 0.f;
 
@@ -105,10 +116,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * d);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[kMaxChunks][8], g[kMaxChunks][8];
+    float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float xv[8], dv[8];
@@ -132,7 +143,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
     const uint4* rr = dx_resid ? reinterpret_cast<const uint4*>(dx_resid + row * d) : nullptr;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float o[8];
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const __nv_bfloat16*
   }
   // block reduce of the per-lane column partials, then one atomic per column per block
 #pragma unroll
-  for (int c = 0; c < kMaxChunks; ++c) {
+  for (int c = 0; c < NCH; ++c) {
     const int ci = lane + c * 32;
     if (ci < nchunk) {
 #pragma unroll
@@ -355,16 +366,17 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const __nv_bfloat16* 
 // ------------------------------------------------------------------------------------------------
 // F.normalize (model.py:391): warp per row
 // ------------------------------------------------------------------------------------------------
+template <int NCH>
 __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          float* __restrict__ inv_norm, int64_t rows, int d) {
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nchunk = d >> 3;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
-    float v[kMaxChunks][8];
+    float v[NCH][8];
     float sq = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         unpack_bf16x8(xr[ci], v[c]);
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const __nv_bfloat16* __
     const float inv = 1.f / fmaxf(sqrtf(warp_sum(sq)), 1e-12f);
     uint4* yr = reinterpret_cast<uint4*>(y + row * d);
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float o[8];
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(256) l2norm_fwd_kernel(const __nv_bfloat16* __
   }
 }
 
-template <bool DY_F32>
+template <bool DY_F32, int NCH>
 __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const void* __restrict__ dy_, const __nv_bfloat16* __restrict__ y,
                                                          const float* __restrict__ inv_norm, __nv_bfloat16* __restrict__ dx,
                                                          int64_t rows, int d) {
@@ -396,10 +408,10 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const void* __restrict_
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
     const uint4* yr = reinterpret_cast<const uint4*>(y + row * d);
-    float yv[kMaxChunks][8], gv[kMaxChunks][8];
+    float yv[NCH][8], gv[NCH][8];
     float dot = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         unpack_bf16x8(yr[ci], yv[c]);
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(256) l2norm_bwd_kernel(const void* __restrict_
     const float inv = inv_norm[row];
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float o[8];
@@ -486,7 +498,10 @@ extern "C" int clipn_layernorm_fwd(const void* x, const float* gamma, const floa
   CLIPN_REQUIRE(x && gamma && beta && y, "layernorm_fwd: null pointer");
   CLIPN_REQUIRE(d % 8 == 0 && d <= 1024 && d > 0, "layernorm: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return CLIPN_OK;
-  layernorm_fwd_kernel<<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(BF(x), gamma, beta, BFW(y), mean, rstd, rows, d, eps);
+#define CLIPN_LN_FWD(N) \
+  layernorm_fwd_kernel<N><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(BF(x), gamma, beta, BFW(y), mean, rstd, rows, d, eps)
+  CLIPN_DISPATCH_NCH(d, CLIPN_LN_FWD);
+#undef CLIPN_LN_FWD
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }
@@ -498,10 +513,14 @@ extern "C" int clipn_layernorm_bwd(const void* dy, const void* x, const float* m
   CLIPN_REQUIRE(d % 8 == 0 && d <= 1024 && d > 0, "layernorm: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return CLIPN_OK;
   int64_t blocks = (rows + 7) / 8;
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * (d <= 512 ? 3 : 2);  // one resident wave: every block does a single dgamma/dbeta flush
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-  layernorm_bwd_kernel<<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(BF(dy), BF(x), mean, rstd, gamma, BF(dx_resid),
-                                                                          BFW(dx_out), dgamma, dbeta, rows, d);
+#define CLIPN_LN_BWD(N)                                                                                              \
+  layernorm_bwd_kernel<N><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(BF(dy), BF(x), mean, rstd, gamma,          \
+                                                                             BF(dx_resid), BFW(dx_out), dgamma, dbeta, \
+                                                                             rows, d)
+  CLIPN_DISPATCH_NCH(d, CLIPN_LN_BWD);
+#undef CLIPN_LN_BWD
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }
@@ -591,7 +610,9 @@ extern "C" int clipn_scatter_rows(const void* dpooled, const int32_t* idx, void*
 extern "C" int clipn_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int32_t d, clipn_stream_t stream) {
   CLIPN_REQUIRE(x && y && d % 8 == 0 && d <= 1024, "l2norm_fwd: bad arguments");
   if (rows <= 0) return CLIPN_OK;
-  l2norm_fwd_kernel<<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(BF(x), BFW(y), inv_norm, rows, d);
+#define CLIPN_L2_FWD(N) l2norm_fwd_kernel<N><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(BF(x), BFW(y), inv_norm, rows, d)
+  CLIPN_DISPATCH_NCH(d, CLIPN_L2_FWD);
+#undef CLIPN_L2_FWD
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }
@@ -600,10 +621,13 @@ extern "C" int clipn_l2norm_bwd(const void* dy, int32_t dy_is_f32, const void* y
                                 int64_t rows, int32_t d, clipn_stream_t stream) {
   CLIPN_REQUIRE(dy && y && inv_norm && dx && d % 8 == 0 && d <= 1024, "l2norm_bwd: bad arguments");
   if (rows <= 0) return CLIPN_OK;
-  if (dy_is_f32)
-    l2norm_bwd_kernel<true><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(dy, BF(y), inv_norm, BFW(dx), rows, d);
-  else
-    l2norm_bwd_kernel<false><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(dy, BF(y), inv_norm, BFW(dx), rows, d);
+#define CLIPN_L2_BWD(N)                                                                                                 \
+  if (dy_is_f32)                                                                                                        \
+    l2norm_bwd_kernel<true, N><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(dy, BF(y), inv_norm, BFW(dx), rows, d);  \
+  else                                                                                                                  \
+    l2norm_bwd_kernel<false, N><<<grid_for_rows(rows, 8), 256, 0, ST(stream)>>>(dy, BF(y), inv_norm, BFW(dx), rows, d)
+  CLIPN_DISPATCH_NCH(d, CLIPN_L2_BWD);
+#undef CLIPN_L2_BWD
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }

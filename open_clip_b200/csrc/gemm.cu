@@ -1,11 +1,14 @@
 // tcgen05 / TMEM / TMA GEMM family for the CLIP towers and the contrastive-loss logits.
 //
 // One persistent, warp-specialised kernel (1 CTA per SM, 384 threads):
-//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4-6 stage mbarrier ring)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 3-6 stage mbarrier ring)
 //   warp 1      : MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, M=128 x N=BN x K=16,
 //                                 fp32 accumulators double-buffered in TMEM: 2 x BN columns)
 //   warp 2      : TMEM allocator
-//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> global)
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b.x32 -> registers -> fused epilogue -> per-warp swizzled smem
+//                                 staging tile -> TMA store; residual / pre-activation operands arrive by TMA load
+//                                 into the same staging tile, so all global traffic of the epilogue is coalesced
+//                                 bulk copies and no cross-warp synchronisation exists in the epilogue)
 // Operands may be K-major (torch Linear layout) or MN-major (weight-gradient / `x @ W` layouts); the
 // MN-major case uses the canonical ((8,n),(8,k)) SW128 layout with LBO = 8 KiB between 64-wide MN groups.
 // The B operand may be split across up to 8 tensor maps (one per rank's peer-mapped feature buffer), which
@@ -25,20 +28,37 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiWarps * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int EPI_BUF_BYTES = 32 * 128;  // one warp's staging tile: 32 rows x 64 bf16 (128 B, SW128)
 constexpr float kLog2e = 1.4426950408889634f;
 
-template <int BN>
+// what each epilogue reads / writes through the per-warp TMA staging tiles
+template <int EPI>
+struct EpiTraits {
+  static constexpr bool kOutTma = EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_BIAS_GELU || EPI == CLIPN_EPI_BIAS_RESID ||
+                                  EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_CLIP_DLOGITS || EPI == CLIPN_EPI_SIGLIP;
+  static constexpr int kNumOut = (EPI == CLIPN_EPI_BIAS_GELU || EPI == CLIPN_EPI_DGELU) ? 2 : 1;
+  static constexpr bool kAux = EPI == CLIPN_EPI_BIAS_RESID || EPI == CLIPN_EPI_DGELU;
+  static constexpr bool kRedF32 = EPI == CLIPN_EPI_ACCUM_F32;  // fp32 tile reduce-added by TMA (cp.reduce.async.bulk)
+  static constexpr int kBufs = kOutTma ? kNumOut : (kRedF32 ? 1 : 0);
+};
+
+template <int BN, int EPI>
 struct TileCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int EPI_BYTES = kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 KB / 64 KB
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
+  static constexpr int STAGES_FIT = (BUDGET - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + kEpiWarps) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
 };
 
 // ---------------------------------------------------------------------------------------------------
-// Epilogues. Each epilogue thread owns one output row; it receives 32 consecutive columns at a time.
+// Epilogue math. Each epilogue thread owns one output row; it receives 32 consecutive columns at a time.
 // ---------------------------------------------------------------------------------------------------
 struct EpiState {
   float run_max, run_sum, pos, acc0, acc1;
@@ -89,9 +109,35 @@ __device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b
   }
 }
 
-// row/col are global output coordinates; caller guarantees col < N (warp-uniform), row may be >= M.
+// Staging tile access: row r (0..31) of a 1024-aligned 32x128B SW128 tile, 16-byte chunk c (0..7).
+__device__ __forceinline__ uint4* stage_chunk(uint8_t* buf, int r, int c) {
+  return reinterpret_cast<uint4*>(buf + r * 128 + ((c ^ (r & 7)) << 4));
+}
+__device__ __forceinline__ void stage_write32(uint8_t* buf, int r, int half, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[i * 8 + j];
+    *stage_chunk(buf, r, half * 4 + i) = pack_bf16x8(t);
+  }
+}
+__device__ __forceinline__ void stage_read32(uint8_t* buf, int r, int half, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+    unpack_bf16x8(*stage_chunk(buf, r, half * 4 + i), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i * 8 + j] = t[j];
+  }
+}
+
+// v: accumulator chunk in, primary bf16 output out (when the epilogue has one); aux: residual / pre-activation
+// values (EpiTraits::kAux); o1: second output (kNumOut == 2).  fp32 outputs / atomics / reductions are issued here.
+// Caller guarantees col < N (warp-uniform); row may be >= M.
 template <int EPI>
-__device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col, float (&v)[32], EpiState& st) {
+__device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int col, float (&v)[32],
+                                            const float (&aux)[32], float (&o1)[32], EpiState& st) {
   const bool row_ok = row < p.m;
   const int nvalid = (p.n - col) < 32 ? (p.n - col) : 32;
   if constexpr (EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_STORE_F32) {
@@ -103,10 +149,8 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += b[i];
     }
-    if (row_ok) {
-      if constexpr (EPI == CLIPN_EPI_STORE) {
-        store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
-      } else {
+    if constexpr (EPI == CLIPN_EPI_STORE_F32) {
+      if (row_ok) {
         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -116,45 +160,25 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
   } else if constexpr (EPI == CLIPN_EPI_BIAS_GELU) {
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
-    float g[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       v[i] = bf16_round(v[i] + b[i]);
-      g[i] = gelu_exact(v[i]);
-    }
-    if (row_ok) {
-      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
-      store_bf16_row32(p.c2, p.ldc2, row, col, g, nvalid);
+      o1[i] = gelu_exact(v[i]);
     }
   } else if constexpr (EPI == CLIPN_EPI_BIAS_RESID) {
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
-    if (row_ok) {
-      float r[32];
-      load_bf16_row32(p.aux, p.ldaux, row, col, r, nvalid);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + b[i]) + r[i];
-      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
-    }
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + b[i]) + aux[i];
   } else if constexpr (EPI == CLIPN_EPI_DGELU) {
-    if (row_ok) {
-      float h[32], g[32];
-      load_bf16_row32(p.aux, p.ldaux, row, col, h, nvalid);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        v[i] = v[i] * gelu_grad(h[i]);
-        g[i] = gelu_exact(h[i]);
-      }
-      store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
-      store_bf16_row32(p.c2, p.ldc2, row, col, g, nvalid);
+    for (int i = 0; i < 32; ++i) {
+      v[i] = v[i] * gelu_grad(aux[i]);
+      o1[i] = gelu_exact(aux[i]);
     }
   } else if constexpr (EPI == CLIPN_EPI_ACCUM_F32) {
-    if (row_ok) {
-      float* dst = reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col;
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (i < nvalid) atomicAdd(dst + i, v[i] * p.alpha);
-    }
+    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;  // reduce-added to C by the caller (TMA in the tensor-core path)
   } else if constexpr (EPI == CLIPN_EPI_LSE) {
     const int label = row + p.label_offset;
     float cmax = -INFINITY;
@@ -176,26 +200,25 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
   } else if constexpr (EPI == CLIPN_EPI_CLIP_DLOGITS) {
     const int label = row + p.label_offset;
     const float rl = row_ok ? __ldg(p.row_lse + row) : 0.f;
-    float g[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float s = v[i] * p.alpha + p.logit_bias;
+      const float dot = v[i];
+      const float s = dot * p.alpha + p.logit_bias;
       const float pr = exp2f((s - rl) * kLog2e);
       const float pc =
           (p.col_w != 0.f && i < nvalid) ? p.col_w * exp2f((s - __ldg(p.col_lse + col + i)) * kLog2e) : 0.f;
       const float onehot = (col + i == label) ? 1.f : 0.f;
-      g[i] = p.gscale * (pr + pc - (1.f + p.col_w) * onehot);
+      v[i] = p.gscale * (pr + pc - (1.f + p.col_w) * onehot);
       if (row_ok && i < nvalid) {
-        st.acc0 += (pr - onehot) * v[i];
+        st.acc0 += (pr - onehot) * dot;
         st.acc1 += (pr - onehot);
       }
     }
-    if (row_ok) store_bf16_row32(p.c, p.ldc, row, col, g, nvalid);
   } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
-    float g[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const float z = v[i] * p.alpha + p.logit_bias;
+      const float dot = v[i];
+      const float z = dot * p.alpha + p.logit_bias;
       const float y = (!p.negative_only && (col + i == row + p.label_offset)) ? 1.f : -1.f;
       const float yz = y * z;
       // -logsigmoid(yz) = softplus(-yz) = max(-yz,0) + log1p(exp(-|yz|))
@@ -204,14 +227,13 @@ __device__ __forceinline__ void epi_apply(const GemmParams& p, int row, int col,
       // d/dz = -y * sigmoid(-yz)
       const float sig = (yz >= 0.f) ? e / (1.f + e) : 1.f / (1.f + e);
       const float dz = -y * sig;
-      g[i] = p.gscale * dz;
+      v[i] = p.gscale * dz;
       if (row_ok && i < nvalid) {
         st.run_sum += loss;
-        st.acc0 += dz * v[i];
+        st.acc0 += dz * dot;
         st.acc1 += dz;
       }
     }
-    if (row_ok && p.c != nullptr) store_bf16_row32(p.c, p.ldc, row, col, g, nvalid);
   }
 }
 
@@ -248,17 +270,20 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, int row, int sla
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EPI>;
+  using Tr = EpiTraits<EPI>;
   GemmParams p = p_in;
   if (p.alpha_dev != nullptr) p.alpha *= __ldg(p.alpha_dev);
   if (p.logit_bias_dev != nullptr) p.logit_bias += __ldg(p.logit_bias_dev);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_smem = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar = tmem_empty + 2;  // one per epilogue warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -266,6 +291,9 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm.a);
     for (int i = 0; i < p.b_maps; ++i) tma_prefetch_desc(&tm.b[i]);
+    if (Tr::kOutTma || Tr::kRedF32) tma_prefetch_desc(&tm.c);
+    if (Tr::kNumOut == 2) tma_prefetch_desc(&tm.c2);
+    if (Tr::kAux) tma_prefetch_desc(&tm.aux);
   }
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < Cfg::STAGES; ++i) {
@@ -276,6 +304,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], kEpiWarps);
     }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -371,8 +400,11 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
     const int e = warp - 4;
     const int q = e & 3;   // TMEM lane quarter == warp % 4
     const int h = e >> 2;  // column half of the tile
+    uint8_t* buf0 = epi_smem + e * (Tr::kBufs * EPI_BUF_BYTES);
+    uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
+    const bool store_c = Tr::kOutTma && (EPI != CLIPN_EPI_SIGLIP || p.c != nullptr);
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
       const int tile = w / p.splits;
       const int tn = tile % p.tiles_n;
@@ -380,15 +412,63 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       const int n0 = tn * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const int row0 = m0 + q * 32;
+      const int row = row0 + lane;
       EpiState st;
       epi_begin(st);
 #pragma unroll 1
-      for (int j = 0; j < BN / 64; ++j) {
-        const int cl = h * (BN / 2) + j * 32;
-        float v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cl, v);
-        if (n0 + cl < p.n) epi_apply<EPI>(p, row, n0 + cl, v, st);
+      for (int jc = 0; jc < BN / 128; ++jc) {
+        const int cl0 = h * (BN / 2) + jc * 64;  // first column (within the tile) of this 64-wide chunk
+        const bool chunk_live = n0 + cl0 < p.n;  // warp-uniform
+        if (Tr::kOutTma && chunk_live) {
+          // staging tiles must be free: the TMA stores of the previous chunk have finished reading them
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          if (Tr::kAux) {
+            if (lane == 0) {
+              mbar_expect_tx(&aux_bar[e], EPI_BUF_BYTES);
+              tma_load_2d(buf0, &tm.aux, &aux_bar[e], n0 + cl0, row0);
+            }
+            mbar_wait(&aux_bar[e], aux_phase);
+            aux_phase ^= 1;
+          }
+        }
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int cl = cl0 + half * 32;
+          float v[32], aux[32], o1[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cl, v);
+          if (n0 + cl < p.n) {
+            if (Tr::kAux) stage_read32(buf0, lane, half, aux);
+            epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
+            if (store_c) stage_write32(buf0, lane, half, v);
+            if (Tr::kNumOut == 2) stage_write32(buf1, lane, half, o1);
+            if (Tr::kRedF32) {
+              // fp32 32x32 tile -> swizzled staging -> cp.reduce.async.bulk.tensor (.add) into C
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<float4*>(stage_chunk(buf0, lane, i)) =
+                    make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_reduce_add_2d(&tm.c, buf0, n0 + cl, row0);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+        if (Tr::kOutTma && chunk_live && store_c) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm.c, buf0, n0 + cl0, row0);
+            if (Tr::kNumOut == 2) tma_store_2d(&tm.c2, buf1, n0 + cl0, row0);
+            tma_store_commit();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -397,6 +477,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if ((Tr::kOutTma || Tr::kRedF32) && lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -406,11 +487,12 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// CUDA-core restatement (tests only): identical slab structure and epilogues, no tensor cores.
-// grid = (ceil(M/128), tiles_n*2), block = 128 threads (thread == row).
+// CUDA-core restatement (tests only): identical slab structure and epilogue math, no tensor cores, plain
+// global loads/stores.  grid = (ceil(M/128), tiles_n*2), block = 128 threads (thread == row).
 // ---------------------------------------------------------------------------------------------------
 template <int EPI>
 __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) {
+  using Tr = EpiTraits<EPI>;
   GemmParams p = p_in;
   if (p.alpha_dev != nullptr) p.alpha *= __ldg(p.alpha_dev);
   if (p.logit_bias_dev != nullptr) p.logit_bias += __ldg(p.logit_bias_dev);
@@ -418,19 +500,21 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
   const int slab = blockIdx.y;
   const int n_begin = (slab >> 1) * bn + (slab & 1) * (bn / 2);
   const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(ops.a);
+  const bool store_c = Tr::kOutTma && (EPI != CLIPN_EPI_SIGLIP || p.c != nullptr);
   EpiState st;
   epi_begin(st);
   for (int cl = 0; cl < bn / 2; cl += 32) {
     const int col = n_begin + cl;
     if (col >= p.n) break;
-    float v[32];
+    const int nvalid = (p.n - col) < 32 ? (p.n - col) : 32;
+    float v[32], aux[32], o1[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+    for (int i = 0; i < 32; ++i) v[i] = aux[i] = o1[i] = 0.f;
     if (row < p.m) {
       for (int k = 0; k < p.k; ++k) {
         const float a = __bfloat162float(p.a_mn ? A[static_cast<int64_t>(k) * ops.lda + row]
                                                   : A[static_cast<int64_t>(row) * ops.lda + k]);
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < nvalid; ++i) {
           const int n = col + i;
           float b;
           if (!p.b_mn) {
@@ -445,8 +529,17 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
           v[i] += a * b;
         }
       }
+      if (Tr::kAux) load_bf16_row32(p.aux, p.ldaux, row, col, aux, nvalid);
     }
-    epi_apply<EPI>(p, row, col, v, st);
+    epi_compute<EPI>(p, row, col, v, aux, o1, st);
+    if (row < p.m) {
+      if (Tr::kRedF32) {
+        float* dst = reinterpret_cast<float*>(p.c) + static_cast<int64_t>(row) * p.ldc + col;
+        for (int i = 0; i < nvalid; ++i) atomicAdd(dst + i, v[i]);
+      }
+      if (store_c) store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
+      if (Tr::kNumOut == 2) store_bf16_row32(p.c2, p.ldc2, row, col, o1, nvalid);
+    }
   }
   epi_finish<EPI>(p, row, slab, st);
 }
@@ -458,7 +551,7 @@ int gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : 128; }
 
 template <int BN, int EPI>
 static int launch_tc(const TmapSet& tm, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, EPI>;
   static bool configured = false;  // benign race: idempotent attribute set
   if (!configured) {
     CLIPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -563,6 +656,25 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
       const uint64_t rows = b_maps > 1 ? static_cast<uint64_t>(b_rows_per_map) : static_cast<uint64_t>(d.k);
       rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.n, rows, d.ldb * 2, 64, BK, 128);
     }
+    if (rc) return rc;
+  }
+  // epilogue staging maps: 64-column x 32-row bf16 boxes (one warp's tile), SW128
+  const bool out_tma = ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID ||
+                       ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_CLIP_DLOGITS || (ep == CLIPN_EPI_SIGLIP && d.c != nullptr);
+  if (out_tma) {
+    rc = make_tmap_2d(&tm.c, d.c, 2, d.n, d.m, d.ldc * 2, 64, 32, 128);
+    if (rc) return rc;
+  }
+  if (ep == CLIPN_EPI_ACCUM_F32) {
+    rc = make_tmap_2d(&tm.c, d.c, 4, d.n, d.m, d.ldc * 4, 32, 32, 128);
+    if (rc) return rc;
+  }
+  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU) {
+    rc = make_tmap_2d(&tm.c2, d.c2, 2, d.n, d.m, d.ldc2 * 2, 64, 32, 128);
+    if (rc) return rc;
+  }
+  if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU) {
+    rc = make_tmap_2d(&tm.aux, d.aux, 2, d.n, d.m, d.ldaux * 2, 64, 32, 128);
     if (rc) return rc;
   }
 #define CLIPN_TC_CASE(E) \

@@ -9,6 +9,7 @@ constexpr int kMaxBMaps = 8;
 struct alignas(64) TmapSet {
   CUtensorMap a;
   CUtensorMap b[kMaxBMaps];
+  CUtensorMap c, c2, aux;  // epilogue staging maps (64-col x 32-row bf16 boxes)
 };
 
 struct GemmParams {

@@ -98,8 +98,16 @@ def wgrad_splits(m_out: int, n_out: int, k: int) -> int:
     bn = L.lib().clipn_gemm_tile_n(n_out)
     tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
     kblocks = (k + 63) // 64
-    s = max(1, (3 * 148 + tiles - 1) // tiles)
-    return max(1, min(s, kblocks // 4 if kblocks >= 8 else 1))
+    sms = 148
+    best, best_util = 1, 0.0
+    for s in range(1, 33):
+        if s > 1 and kblocks // s < 16:   # keep >= 16 k-blocks (1024 rows) per work item
+            break
+        items = tiles * s
+        util = items / (((items + sms - 1) // sms) * sms)
+        if util > best_util + 0.02:       # prefer fewer splits (fewer reduce-adds) unless utilisation clearly improves
+            best, best_util = s, util
+    return best
 
 
 def layernorm_fwd(x, gamma, beta, out=None, eps: float = 1e-5, save_stats: bool = True):
