@@ -118,7 +118,7 @@ __device__ __forceinline__ void stage_frag_tile(__nv_bfloat16* stage, const floa
 template <int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, (MAXW <= 5) ? 3 : 2)
 attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
-                     float* __restrict__ lse_out, int items, int seq, int heads, int causal, float scale) {
+                     float* __restrict__ lse_out, int items, int seq, int heads, int causal, float scale, int nstages) {
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Lp = (seq + 15) & ~15;
   const int stage_elems = 3 * Lp * LDS;
@@ -128,7 +128,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const float sl2 = scale * kLog2e;
 
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < nstages; ++s)
     for (int t = 0; t < 3; ++t) tile_zero_pad(sbase + s * stage_elems + t * Lp * LDS, seq, Lp);
 
   auto prefetch = [&](int item, int s) {
@@ -141,14 +141,19 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   };
 
   int item = blockIdx.x;
-  if (item < items) prefetch(item, 0);
+  if (nstages == 2 && item < items) prefetch(item, 0);
   cp_async_commit();
   for (int it = 0; item < items; item += gridDim.x, ++it) {
-    const int s = it & 1;
+    const int s = (nstages == 2) ? (it & 1) : 0;
     const int next = item + gridDim.x;
-    if (next < items) prefetch(next, s ^ 1);
+    if (nstages == 2) {
+      if (next < items) prefetch(next, s ^ 1);
+    } else {
+      prefetch(item, 0);  // long sequences: one stage, no lookahead
+    }
     cp_async_commit();
-    cp_async_wait<1>();
+    if (nstages == 2) cp_async_wait<1>();
+    else cp_async_wait<0>();
     __syncthreads();
     __nv_bfloat16* sQ = sbase + s * stage_elems;
     const __nv_bfloat16* sK = sQ + Lp * LDS;
@@ -246,20 +251,20 @@ template <int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 2)
 attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                      const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, int items, int seq, int heads,
-                     int causal, float scale) {
+                     int causal, float scale, int nstages) {
   extern __shared__ __align__(16) uint8_t smem_att[];
   const int Lp = (seq + 15) & ~15;
   const int stage_elems = 4 * Lp * LDS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   __nv_bfloat16* sbase = reinterpret_cast<__nv_bfloat16*>(smem_att);
-  __nv_bfloat16* sOut = sbase + 2 * stage_elems + warp * 16 * LDS;  // per-warp output staging tile
-  float* sLse = reinterpret_cast<float*>(sbase + 2 * stage_elems + nwarps * 16 * LDS);  // log2-domain LSE
+  __nv_bfloat16* sOut = sbase + nstages * stage_elems + warp * 16 * LDS;  // per-warp output staging tile
+  float* sLse = reinterpret_cast<float*>(sbase + nstages * stage_elems + nwarps * 16 * LDS);  // log2-domain LSE
   float* sD = sLse + Lp;
   const int d = heads * HD;
   const int64_t ld = 3 * static_cast<int64_t>(d);
   const float sl2 = scale * kLog2e;
 
-  for (int s = 0; s < 2; ++s)
+  for (int s = 0; s < nstages; ++s)
     for (int t = 0; t < 4; ++t) tile_zero_pad(sbase + s * stage_elems + t * Lp * LDS, seq, Lp);
 
   auto prefetch = [&](int item, int s) {
@@ -273,17 +278,22 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   };
 
   int item = blockIdx.x;
-  if (item < items) prefetch(item, 0);
+  if (nstages == 2 && item < items) prefetch(item, 0);
   cp_async_commit();
   for (int it = 0; item < items; item += gridDim.x, ++it) {
-    const int s = it & 1;
+    const int s = (nstages == 2) ? (it & 1) : 0;
     const int next = item + gridDim.x;
-    if (next < items) prefetch(next, s ^ 1);
+    if (nstages == 2) {
+      if (next < items) prefetch(next, s ^ 1);
+    } else {
+      prefetch(item, 0);  // long sequences: one stage, no lookahead
+    }
     cp_async_commit();
     const int b = item / heads, h = item % heads;
     for (int i = threadIdx.x; i < Lp; i += blockDim.x)
       sLse[i] = (i < seq) ? lse_in[(static_cast<int64_t>(b) * heads + h) * seq + i] * kLog2e : 0.f;
-    cp_async_wait<1>();
+    if (nstages == 2) cp_async_wait<1>();
+    else cp_async_wait<0>();
     __syncthreads();
     const __nv_bfloat16* sQ = sbase + s * stage_elems;
     const __nv_bfloat16* sK = sQ + Lp * LDS;
@@ -434,8 +444,10 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_fwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
   const int Lp = (seq + 15) & ~15;
-  const size_t smem = static_cast<size_t>(2) * 3 * Lp * LDS * 2;
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_fwd: sequence too long for the in-smem kernel (L <= 256)");
+  const size_t stage_bytes = static_cast<size_t>(3) * Lp * LDS * 2;
+  const int nst = (2 * stage_bytes <= 113 * 1024) ? 2 : 1;  // double-buffer when two CTAs still fit per SM
+  const size_t smem = nst * stage_bytes;
+  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_fwd: sequence too long for the in-smem kernel (L <= 512)");
   const int items = batch * heads;
   const int nw = pick_warps(seq);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -449,12 +461,12 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
     CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attention_fwd_kernel<5><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, items, seq, heads,
-                                                         causal, scale);
+                                                         causal, scale, nst);
   } else {
     CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attention_fwd_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<__nv_bfloat16*>(out), lse, items, seq, heads,
-                                                         causal, scale);
+                                                         causal, scale, nst);
   }
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
@@ -469,9 +481,11 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   if (batch <= 0) return CLIPN_OK;
   const int Lp = (seq + 15) & ~15;
   const int nw = pick_warps(seq);
-  const size_t smem = static_cast<size_t>(2) * 4 * Lp * LDS * 2 + static_cast<size_t>(nw) * 16 * LDS * 2 +
-                      static_cast<size_t>(2) * Lp * sizeof(float);
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_bwd: sequence too long for the in-smem kernel (L <= 192)");
+  const size_t stage_bytes = static_cast<size_t>(4) * Lp * LDS * 2;
+  const size_t extra = static_cast<size_t>(nw) * 16 * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);
+  const int nst = (2 * stage_bytes + extra <= 113 * 1024) ? 2 : 1;
+  const size_t smem = nst * stage_bytes + extra;
+  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_bwd: sequence too long for the in-smem kernel (L <= 384)");
   const int items = batch * heads;
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
@@ -484,13 +498,13 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
     attention_bwd_kernel<5><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<const __nv_bfloat16*>(dout), lse,
                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads, causal,
-                                                         scale);
+                                                         scale, nst);
   } else {
     CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attention_bwd_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                          reinterpret_cast<const __nv_bfloat16*>(dout), lse,
                                                          reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads, causal,
-                                                         scale);
+                                                         scale, nst);
   }
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;

@@ -230,9 +230,32 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
   u.w = pack_bf16x2(f[6], f[7]);
   return u;
 }
-__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad(float x) {
-  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+// erf-GELU (nn.GELU(), model.py:183) and its derivative with ONE exp and ONE reciprocal per element:
+// erf(z) = 1 - (a1 t + ... + a5 t^5) e^{-z^2}, t = 1/(1 + p z), z >= 0 (Abramowitz & Stegun 7.1.26, |err| <= 1.5e-7,
+// three orders of magnitude below the bf16 rounding of the result).  e^{-z^2} with z = x/sqrt(2) is also the
+// Gaussian the derivative needs, so the backward costs two more FMAs.  ~18 issue slots per element instead of ~60
+// for erff() + expf(): the GELU epilogues were issue-bound, not tensor-bound (profiles/ round 1).
+__device__ __forceinline__ void gelu_core(float x, float& half_one_plus_erf, float& gauss) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  gauss = exp2f(-z * z * 1.4426950408889634f);  // e^{-x^2/2}
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, gauss, 1.0f);  // erf(|x|/sqrt2) in [0,1]
+  half_one_plus_erf = fmaf(copysignf(0.5f, x), erf_abs, 0.5f);
+}
+__device__ __forceinline__ float gelu_exact(float x) {
+  float c, g;
+  gelu_core(x, c, g);
+  return x * c;
+}
+__device__ __forceinline__ void gelu_and_grad(float x, float& gelu, float& grad) {
+  float c, g;
+  gelu_core(x, c, g);
+  gelu = x * c;
+  grad = fmaf(x * 0.3989422804014327f, g, c);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

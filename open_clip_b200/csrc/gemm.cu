@@ -173,8 +173,10 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
   } else if constexpr (EPI == CLIPN_EPI_DGELU) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      v[i] = v[i] * gelu_grad(aux[i]);
-      o1[i] = gelu_exact(aux[i]);
+      float gl, gr;
+      gelu_and_grad(aux[i], gl, gr);
+      v[i] = v[i] * gr;
+      o1[i] = gl;
     }
   } else if constexpr (EPI == CLIPN_EPI_ACCUM_F32) {
 #pragma unroll
