@@ -17,6 +17,7 @@
 // Replaces (reference, cuBLASLt via ATen): transformer.py:195-197,246,295-299,794,923; model.py:409;
 // loss.py:102-110 and the autograd dgrad/wgrad of each.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_internal.cuh"
@@ -42,14 +43,16 @@ struct EpiTraits {
   static constexpr int kBufs = kOutTma ? kNumOut : (kRedF32 ? 1 : 0);
 };
 
-template <int BN, int EPI>
+// CTAS = 1: one CTA computes a 128 x BN tile.  CTAS = 2: a CTA pair (cluster of 2, cta_group::2) computes 256 x BN;
+// each CTA stages its own 128 rows of A and BN/2 rows of B, so a stage is 16 KB + BN*64 B and the ring gets deeper.
+template <int BN, int EPI, int CTAS>
 struct TileCfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (BN / CTAS) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_BYTES = kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 KB / 64 KB
   static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
   static constexpr int STAGES_FIT = (BUDGET - EPI_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + kEpiWarps) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
@@ -272,7 +275,7 @@ __device__ __forceinline__ void epi_finish(const GemmParams& p, int row, int sla
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
-  using Cfg = TileCfg<BN, EPI>;
+  using Cfg = TileCfg<BN, EPI, 1>;
   using Tr = EpiTraits<EPI>;
   GemmParams p = p_in;
   if (p.alpha_dev != nullptr) p.alpha *= __ldg(p.alpha_dev);
@@ -488,6 +491,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+#include "gemm_pair.cuh"
+
 // ---------------------------------------------------------------------------------------------------
 // CUDA-core restatement (tests only): identical slab structure and epilogue math, no tensor cores, plain
 // global loads/stores.  grid = (ceil(M/128), tiles_n*2), block = 128 threads (thread == row).
@@ -553,7 +558,7 @@ int gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : 128; }
 
 template <int BN, int EPI>
 static int launch_tc(const TmapSet& tm, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = TileCfg<BN, EPI>;
+  using Cfg = TileCfg<BN, EPI, 1>;
   static bool configured = false;  // benign race: idempotent attribute set
   if (!configured) {
     CLIPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -564,6 +569,34 @@ static int launch_tc(const TmapSet& tm, const GemmParams& p, cudaStream_t stream
   const int grid = total < num_sms() ? total : num_sms();
   gemm_tc_kernel<BN, EPI><<<grid, kThreads, Cfg::SMEM_BYTES, stream>>>(tm, p);
   CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+template <int BN, int EPI>
+static int launch_tc2(const TmapSet& tm, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = TileCfg<BN, EPI, 2>;
+  static bool configured = false;
+  if (!configured) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int total = p.tiles_m * p.tiles_n * p.splits;  // pair tiles
+  const int max_clusters = num_sms() / 2;
+  const int clusters = total < max_clusters ? total : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLIPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN, EPI>, tm, p));
   return CLIPN_OK;
 }
 
@@ -645,6 +678,15 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   clipn_device_info(&sms, &cc_major, &cc_minor);
   CLIPN_REQUIRE(cc_major == 10, "gemm: the tcgen05 kernels require an sm_100 (B200) device");
 
+  // CTA-pair kernel (256-row tiles, cta_group::2) whenever there are at least two 128-row tiles of work;
+  // CLIPN_GEMM_PAIR=0 forces the single-CTA kernel (A/B testing, bisecting).
+  static const bool pair_enabled = [] {
+    const char* e = getenv("CLIPN_GEMM_PAIR");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  const bool use_pair = pair_enabled && d.m > BM;
+  const int b_box_rows = use_pair ? bn / 2 : bn;  // each CTA of a pair stages half of the B tile
+
   TmapSet tm;
   int rc;
   if (!p.a_mn) rc = make_tmap_2d(&tm.a, d.a, 2, d.k, d.m, d.lda * 2, BK, BM, 128);
@@ -653,7 +695,7 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   for (int i = 0; i < b_maps; ++i) {
     if (!p.b_mn) {
       const uint64_t rows = b_maps > 1 ? static_cast<uint64_t>(b_rows_per_map) : static_cast<uint64_t>(d.n);
-      rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.k, rows, d.ldb * 2, BK, bn, 128);
+      rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.k, rows, d.ldb * 2, BK, b_box_rows, 128);
     } else {
       const uint64_t rows = b_maps > 1 ? static_cast<uint64_t>(b_rows_per_map) : static_cast<uint64_t>(d.k);
       rc = make_tmap_2d(&tm.b[i], b_ptrs[i], 2, d.n, rows, d.ldb * 2, 64, BK, 128);
@@ -678,6 +720,13 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU) {
     rc = make_tmap_2d(&tm.aux, d.aux, 2, d.n, d.m, d.ldaux * 2, 64, 32, 128);
     if (rc) return rc;
+  }
+  if (use_pair) {
+    p.tiles_m = (d.m + 2 * BM - 1) / (2 * BM);
+#define CLIPN_TC2_CASE(E) \
+  return (bn == 256) ? launch_tc2<256, E>(tm, p, stream) : launch_tc2<128, E>(tm, p, stream)
+    CLIPN_DISPATCH_EPI(ep, CLIPN_TC2_CASE)
+#undef CLIPN_TC2_CASE
   }
 #define CLIPN_TC_CASE(E) \
   return (bn == 256) ? launch_tc<256, E>(tm, p, stream) : launch_tc<128, E>(tm, p, stream)
