@@ -49,12 +49,17 @@ template <int BN, int EPI, int CTAS>
 struct TileCfg {
   static constexpr int B_STAGE_BYTES = (BN / CTAS) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_BYTES = kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 KB / 64 KB
+  // Pair kernel, dual-output epilogues (GELU fwd / bwd): per warp 6 x 2 KB tiles (32 rows x 32 cols, SW64):
+  // out0, out1 and aux, each double-buffered, so the TMA stores of piece i and the aux TMA load of piece i+1
+  // overlap the math of piece i.  Otherwise: kBufs x 4 KB (32 rows x 64 cols, SW128), single-buffered.
+  static constexpr bool kPipedEpi = CTAS == 2 && EpiTraits<EPI>::kNumOut == 2;
+  static constexpr int EPI_BYTES =
+      kPipedEpi ? kEpiWarps * 6 * 2048 : kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 / 64 / 96 KB
   static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
   static constexpr int STAGES_FIT = (BUDGET - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // 512 or 256 (power of two)
-  static constexpr int BAR_BYTES = (2 * STAGES + 4 + kEpiWarps) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 2 * kEpiWarps) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
@@ -491,6 +496,29 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// 32 rows x 32 bf16 (64-byte rows) SWIZZLE_64B staging tile: 16-byte chunk c (0..3) of row r
+__device__ __forceinline__ uint4* stage64_chunk(uint8_t* buf, int r, int c) {
+  return reinterpret_cast<uint4*>(buf + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void stage64_write32(uint8_t* buf, int r, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[i * 8 + j];
+    *stage64_chunk(buf, r, i) = pack_bf16x8(t);
+  }
+}
+__device__ __forceinline__ void stage64_read32(uint8_t* buf, int r, float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float t[8];
+    unpack_bf16x8(*stage64_chunk(buf, r, i), t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[i * 8 + j] = t[j];
+  }
+}
+
 #include "gemm_pair.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -705,8 +733,12 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   // epilogue staging maps: 64-column x 32-row bf16 boxes (one warp's tile), SW128
   const bool out_tma = ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID ||
                        ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_CLIP_DLOGITS || (ep == CLIPN_EPI_SIGLIP && d.c != nullptr);
+  // pair kernel + two-output epilogue: 32-column pieces (64-byte rows, SW64), see TileCfg::kPipedEpi
+  const bool piped = use_pair && (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU);
+  const uint32_t ebox = piped ? 32 : 64;
+  const int esw = piped ? 64 : 128;
   if (out_tma) {
-    rc = make_tmap_2d(&tm.c, d.c, 2, d.n, d.m, d.ldc * 2, 64, 32, 128);
+    rc = make_tmap_2d(&tm.c, d.c, 2, d.n, d.m, d.ldc * 2, ebox, 32, esw);
     if (rc) return rc;
   }
   if (ep == CLIPN_EPI_ACCUM_F32) {
@@ -714,11 +746,11 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
     if (rc) return rc;
   }
   if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU) {
-    rc = make_tmap_2d(&tm.c2, d.c2, 2, d.n, d.m, d.ldc2 * 2, 64, 32, 128);
+    rc = make_tmap_2d(&tm.c2, d.c2, 2, d.n, d.m, d.ldc2 * 2, ebox, 32, esw);
     if (rc) return rc;
   }
   if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU) {
-    rc = make_tmap_2d(&tm.aux, d.aux, 2, d.n, d.m, d.ldaux * 2, 64, 32, 128);
+    rc = make_tmap_2d(&tm.aux, d.aux, 2, d.n, d.m, d.ldaux * 2, ebox, 32, esw);
     if (rc) return rc;
   }
   if (use_pair) {

@@ -24,8 +24,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tmem_full = empty_bar + Cfg::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* aux_bar = tmem_empty + 2;  // one per epilogue warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + kEpiWarps);
+  uint64_t* aux_bar = tmem_empty + 2;  // two per epilogue warp (double-buffered aux tiles)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -53,7 +53,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       mbar_init(&tmem_full[i], 1);               // multicast tcgen05.commit
       mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // leader: epilogue warps of both CTAs
     }
-    for (int i = 0; i < kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&aux_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -149,6 +149,79 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
     const int e = warp - 4;
     const int q = e & 3;   // TMEM lane quarter == warp % 4
     const int h = e >> 2;  // column half of the tile
+    if constexpr (Cfg::kPipedEpi) {
+      // ---- software-pipelined epilogue for the two-output GELU variants: 32-column pieces, double-buffered
+      // staging; piece i's TMA stores and piece i+1's aux TMA load are in flight while piece i is computed ----
+      constexpr int NP = BN / 64;  // pieces per warp per tile
+      uint8_t* wb = epi_smem + e * (6 * 2048);
+      uint64_t* abar = aux_bar + 2 * e;
+      auto coords = [&](int w, int i, int& col, int& row0) {
+        const int tile = w / p.splits;
+        col = (tile % p.tiles_n) * BN + h * (BN / 2) + i * 32;
+        row0 = (tile / p.tiles_n) * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
+      };
+      uint32_t pc = 0;  // running piece counter: buffer = pc & 1, aux phase = (pc >> 1) & 1
+      if (Tr::kAux && lane == 0 && cluster_id < total_work) {
+        int col, row0;
+        coords(cluster_id, 0, col, row0);
+        mbar_expect_tx(&abar[0], 2048);
+        tma_load_2d(wb + 8192, &tm.aux, &abar[0], col, row0);
+      }
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        EpiState st;
+        epi_begin(st);
+#pragma unroll 1
+        for (int i = 0; i < NP; ++i, ++pc) {
+          const int b = pc & 1;
+          int col, row0;
+          coords(w, i, col, row0);
+          if (lane == 0) tma_store_wait_read<1>();  // the stores that used buffers `b` two pieces ago have read them
+          __syncwarp();
+          if (Tr::kAux) {
+            if (lane == 0) {
+              int nw = w, ni = i + 1;
+              if (ni == NP) {
+                ni = 0;
+                nw = w + num_clusters;
+              }
+              if (nw < total_work) {
+                int ncol, nrow0;
+                coords(nw, ni, ncol, nrow0);
+                mbar_expect_tx(&abar[b ^ 1], 2048);
+                tma_load_2d(wb + 8192 + (b ^ 1) * 2048, &tm.aux, &abar[b ^ 1], ncol, nrow0);
+              }
+            }
+            mbar_wait(&abar[b], (pc >> 1) & 1);
+          }
+          float v[32], aux[32], o1[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * (BN / 2) + i * 32, v);
+          if (Tr::kAux) stage64_read32(wb + 8192 + b * 2048, lane, aux);
+          if (col < p.n) epi_compute<EPI>(p, row0 + lane, col, v, aux, o1, st);
+          stage64_write32(wb + b * 2048, lane, v);
+          stage64_write32(wb + 4096 + b * 2048, lane, o1);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tm.c, wb + b * 2048, col, row0);  // boxes past N / M are clipped by the TMA unit
+            tma_store_2d(&tm.c2, wb + 4096 + b * 2048, col, row0);
+            tma_store_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+          else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      if (lane == 0) tma_store_wait_all<0>();
+    } else {
     uint8_t* buf0 = epi_smem + e * (Tr::kBufs * EPI_BUF_BYTES);
     uint8_t* buf1 = buf0 + EPI_BUF_BYTES;
     const bool store_c = Tr::kOutTma && (EPI != CLIPN_EPI_SIGLIP || p.c != nullptr);
@@ -229,6 +302,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       if (acc == 0) acc_phase ^= 1;
     }
     if ((Tr::kOutTma || Tr::kRedF32) && lane == 0) tma_store_wait_all<0>();
+    }  // !kPipedEpi
   }
 
   // neither CTA may exit (or free TMEM) while its peer can still read its smem / signal its barriers
