@@ -320,6 +320,7 @@ def main():
                               "flops_per_pair": STEP_GFLOP_PER_PAIR * 1e9},
             "gpu_launches": launches,
             "clocks": clocks,
+            "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
         }
         if e2e is not None:
             out["e2e"] = e2e

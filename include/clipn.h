@@ -53,8 +53,9 @@ enum clipn_epilogue {
                                C2 = bf16(gelu_erf(t))           (c_fc + nn.GELU, transformer.py:295-299) */
   CLIPN_EPI_BIAS_RESID = 2, /* C = bf16( bf16(acc + bias) + aux[m,n] )   (out_proj/c_proj + residual
                                add, transformer.py:328-329)                                               */
-  CLIPN_EPI_DGELU = 3,      /* h = aux[m,n]; C = bf16(acc * gelu'(h)); C2 = bf16(gelu(h))  (GELU bwd fused
-                               into the c_proj dgrad; C2 re-materialises the c_proj wgrad operand)        */
+  CLIPN_EPI_DGELU = 3,      /* h = aux[m,n]; C = bf16(acc * gelu'(h)); optional C2 = bf16(gelu(h))  (GELU bwd
+                               fused into the c_proj dgrad; C2, when given, re-materialises the c_proj wgrad
+                               operand so the forward need not keep it)                                   */
   CLIPN_EPI_ACCUM_F32 = 4,  /* C(f32)[m,n] += alpha*acc   (split-K weight gradient, red.global.add)      */
   CLIPN_EPI_STORE_F32 = 5,  /* C(f32) = alpha*acc (+ bias)                                               */
   CLIPN_EPI_LSE = 6,        /* no C.  Online row log-sum-exp partials of alpha*acc (+logit_bias):

@@ -11,6 +11,8 @@
 // Backward recomputes P from the saved log-sum-exp and uses D_i = sum_j P_ij dP_ij (== rowsum(dO o O)), so the
 // forward output is never re-read: phase 1 (warp = 16 queries) computes D, phase 2a dQ, phase 2b (warp = 16 keys,
 // transposed tiles) dK and dV — no atomics, deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace clipn {
@@ -429,6 +431,148 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward, short sequences (L <= 80: CLIP text 77, ViT-B/32 50): P and dS are computed ONCE.
+// Phase A (warp = 16 queries) keeps S/dP of its whole key range in registers (NT n-tiles of 8 keys), reduces
+// D = rowsum(P o dP), forms dS, accumulates dQ and parks P and dS (bf16, [query][key]) in shared memory.
+// Phase B (warp = 16 keys) reads them back TRANSPOSED with ldmatrix.trans as A-operand fragments, so
+// dV = P^T dO and dK = dS^T Q need no recomputed S^T / dP^T, no exps and no masks: 5 GEMM units instead of 9.
+// (ncu, round 1: the recomputing kernel is issue-bound — 139 M warp instructions, 45 % issue-active, 21 % DRAM.)
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(160, 2)
+attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
+                           const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, int items, int seq,
+                           int heads, int causal, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  constexpr int Lp = NT * 8;    // 64 or 80
+  constexpr int LDP = Lp + 8;   // pitch of the P / dS tiles (bf16): conflict-free ldmatrix rows
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sK = sQ + Lp * LDS;
+  __nv_bfloat16* sV = sK + Lp * LDS;
+  __nv_bfloat16* sDO = sV + Lp * LDS;
+  __nv_bfloat16* sP = sDO + Lp * LDS;
+  __nv_bfloat16* sdS = sP + Lp * LDP;
+  __nv_bfloat16* sOut = sdS + Lp * LDP + warp * 16 * LDS;
+  float* sLse = reinterpret_cast<float*>(sdS + Lp * LDP + nwarps * 16 * LDS);
+  const int d = heads * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(d);
+  const float sl2 = scale * kLog2e;
+
+  for (int t = 0; t < 4; ++t) tile_zero_pad(sQ + t * Lp * LDS, seq, Lp);
+
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    tile_cp_async(sQ, base, ld, seq);
+    tile_cp_async(sK, base + d, ld, seq);
+    tile_cp_async(sV, base + 2 * d, ld, seq);
+    tile_cp_async(sDO, dout + static_cast<int64_t>(b) * seq * d + h * HD, d, seq);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < Lp; i += blockDim.x)
+      sLse[i] = (i < seq) ? lse_in[(static_cast<int64_t>(b) * heads + h) * seq + i] * kLog2e : 0.f;
+    cp_async_wait<0>();
+    __syncthreads();
+    __nv_bfloat16* dq_base = dqkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+
+    // ---------------- phase A: warp owns 16 queries ----------------
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      uint32_t qa[4][4], doa[4][4];
+      load_a_frags(sQ, r0, lane, qa);
+      load_a_frags(sDO, r0, lane, doa);
+      const int row_a = r0 + (lane >> 2);
+      const float lse_r[2] = {sLse[row_a], sLse[row_a + 8]};
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      float p[NT][4], dp[NT][4];
+      float dsum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dp[j][e] = 0.f;
+        if (j * 8 < kv_end) {
+          mma_a_tT(sc, qa, sK, j * 8, lane);
+          mma_a_tT(dp[j], doa, sV, j * 8, lane);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = j * 8 + (lane & 3) * 2 + (e & 1);
+          const int row = row_a + (e >> 1) * 8;
+          const bool ok = key < kv_end && row < seq && !(causal && key > row);
+          p[j][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) : 0.f;
+          dsum[e >> 1] += p[j][e] * dp[j][e];
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        dsum[t] += __shfl_xor_sync(0xffffffffu, dsum[t], 1);
+        dsum[t] += __shfl_xor_sync(0xffffffffu, dsum[t], 2);
+      }
+      float dq[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) ds[e] = p[j][e] * (dp[j][e] - dsum[e >> 1]);
+        const int c = j * 8 + (lane & 3) * 2;
+        *reinterpret_cast<uint32_t*>(sP + row_a * LDP + c) = pack_bf16x2(p[j][0], p[j][1]);
+        *reinterpret_cast<uint32_t*>(sP + (row_a + 8) * LDP + c) = pack_bf16x2(p[j][2], p[j][3]);
+        *reinterpret_cast<uint32_t*>(sdS + row_a * LDP + c) = pack_bf16x2(ds[0], ds[1]);
+        *reinterpret_cast<uint32_t*>(sdS + (row_a + 8) * LDP + c) = pack_bf16x2(ds[2], ds[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dp[j][e] = ds[e];  // dp now holds dS for the dQ MMAs
+      }
+#pragma unroll
+      for (int kk = 0; kk < NT / 2; ++kk) {
+        if (kk * 16 < kv_end) {
+          uint32_t pa[4];
+          pack_frag(pa, dp[2 * kk], dp[2 * kk + 1]);
+          mma_p_t(dq, pa, sK, kk * 16, lane);
+        }
+      }
+      __syncwarp();
+      stage_frag_tile(sOut, dq, scale, scale, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base, ld, r0, seq, lane);
+    }
+    __syncthreads();
+
+    // ---------------- phase B: warp owns 16 keys; P^T and dS^T come from shared memory ----------------
+    for (int c0 = warp * 16; c0 < Lp; c0 += nwarps * 16) {
+      float dk[8][4], dv[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[j][e] = dv[j][e] = 0.f;
+      const int q_begin = causal ? c0 : 0;
+      const int mi = lane >> 3, ri = lane & 7;
+      for (int q0 = q_begin; q0 < seq; q0 += 16) {
+        uint32_t pa[4], da[4];
+        const int off = (q0 + (mi >> 1) * 8 + ri) * LDP + c0 + (mi & 1) * 8;
+        ldmatrix_x4_trans(pa, sP + off);
+        ldmatrix_x4_trans(da, sdS + off);
+        mma_p_t(dv, pa, sDO, q0, lane);
+        mma_p_t(dk, da, sQ, q0, lane);
+      }
+      __syncwarp();
+      stage_frag_tile(sOut, dk, scale, scale, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base + d, ld, c0, seq, lane);
+      __syncwarp();
+      stage_frag_tile(sOut, dv, 1.f, 1.f, lane);
+      __syncwarp();
+      store_tile16(sOut, dq_base + 2 * d, ld, c0, seq, lane);
+    }
+    __syncthreads();  // tiles, sP/sdS and sLse are rewritten by the next item
+  }
+}
+
 static int pick_warps(int seq) {
   int tiles = (seq + 15) / 16;
   return tiles < 8 ? tiles : 8;
@@ -481,6 +625,36 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   if (batch <= 0) return CLIPN_OK;
   const int Lp = (seq + 15) & ~15;
   const int nw = pick_warps(seq);
+  static const bool small_enabled = [] {
+    const char* e = getenv("CLIPN_ATTN_BWD_SMALL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (seq <= 80 && small_enabled) {
+    const int lp = seq <= 64 ? 64 : 80;
+    const size_t smem = (static_cast<size_t>(4) * lp * LDS + static_cast<size_t>(2) * lp * (lp + 8) +
+                         static_cast<size_t>(nw) * 16 * LDS) * 2 + static_cast<size_t>(lp) * sizeof(float);
+    const int items = batch * heads;
+    int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+    if (per_sm > 2) per_sm = 2;
+    int grid = num_sms() * per_sm;
+    if (grid > items) grid = items;
+    auto st = static_cast<cudaStream_t>(stream);
+    if (lp == 64) {
+      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attention_bwd_small_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads,
+                                                                 causal, scale);
+    } else {
+      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attention_bwd_small_kernel<10><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                                                  reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                                                  reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads,
+                                                                  causal, scale);
+    }
+    CLIPN_CHECK_CUDA(cudaGetLastError());
+    return CLIPN_OK;
+  }
   const size_t stage_bytes = static_cast<size_t>(4) * Lp * LDS * 2;
   const size_t extra = static_cast<size_t>(nw) * 16 * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);
   const int nst = (2 * stage_bytes + extra <= 113 * 1024) ? 2 : 1;

@@ -302,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
     tma_prefetch_desc(&tm.a);
     for (int i = 0; i < p.b_maps; ++i) tma_prefetch_desc(&tm.b[i]);
     if (Tr::kOutTma || Tr::kRedF32) tma_prefetch_desc(&tm.c);
-    if (Tr::kNumOut == 2) tma_prefetch_desc(&tm.c2);
+    if (Tr::kNumOut == 2 && p.c2 != nullptr) tma_prefetch_desc(&tm.c2);
     if (Tr::kAux) tma_prefetch_desc(&tm.aux);
   }
   if (warp == 1 && elect_one()) {
@@ -452,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             if (Tr::kAux) stage_read32(buf0, lane, half, aux);
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
-            if (Tr::kNumOut == 2) stage_write32(buf1, lane, half, o1);
+            if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
             if (Tr::kRedF32) {
               // fp32 32x32 tile -> swizzled staging -> cp.reduce.async.bulk.tensor (.add) into C
               if (lane == 0) tma_store_wait_read<0>();
@@ -475,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm.c, buf0, n0 + cl0, row0);
-            if (Tr::kNumOut == 2) tma_store_2d(&tm.c2, buf1, n0 + cl0, row0);
+            if (Tr::kNumOut == 2 && p.c2 != nullptr) tma_store_2d(&tm.c2, buf1, n0 + cl0, row0);
             tma_store_commit();
           }
         }
@@ -573,7 +573,7 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
         for (int i = 0; i < nvalid; ++i) atomicAdd(dst + i, v[i]);
       }
       if (store_c) store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
-      if (Tr::kNumOut == 2) store_bf16_row32(p.c2, p.ldc2, row, col, o1, nvalid);
+      if (Tr::kNumOut == 2 && p.c2 != nullptr) store_bf16_row32(p.c2, p.ldc2, row, col, o1, nvalid);
     }
   }
   epi_finish<EPI>(p, row, slab, st);
@@ -660,8 +660,8 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   const int ep = d.epilogue;
   const bool needs_c = !(ep == CLIPN_EPI_LSE || (ep == CLIPN_EPI_SIGLIP && d.c == nullptr));
   if (needs_c) CLIPN_REQUIRE(d.c != nullptr && d.ldc % 8 == 0, "gemm: C missing or ldc not a multiple of 8");
-  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU)
-    CLIPN_REQUIRE(d.c2 != nullptr && d.ldc2 % 8 == 0, "gemm: C2 required");
+  if (ep == CLIPN_EPI_BIAS_GELU) CLIPN_REQUIRE(d.c2 != nullptr, "gemm: C2 required");
+  if (d.c2 != nullptr) CLIPN_REQUIRE(d.ldc2 % 8 == 0, "gemm: ldc2 must be a multiple of 8");  // DGELU: C2 optional
   if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID) CLIPN_REQUIRE(d.bias != nullptr, "gemm: bias required");
   if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU)
     CLIPN_REQUIRE(d.aux != nullptr && d.ldaux % 8 == 0, "gemm: aux required");
@@ -745,7 +745,7 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
     rc = make_tmap_2d(&tm.c, d.c, 4, d.n, d.m, d.ldc * 4, 32, 32, 128);
     if (rc) return rc;
   }
-  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU) {
+  if ((ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU) && d.c2 != nullptr) {
     rc = make_tmap_2d(&tm.c2, d.c2, 2, d.n, d.m, d.ldc2 * 2, ebox, 32, esw);
     if (rc) return rc;
   }

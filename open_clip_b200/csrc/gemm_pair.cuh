@@ -37,7 +37,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
     tma_prefetch_desc(&tm.a);
     for (int i = 0; i < p.b_maps; ++i) tma_prefetch_desc(&tm.b[i]);
     if (Tr::kOutTma || Tr::kRedF32) tma_prefetch_desc(&tm.c);
-    if (Tr::kNumOut == 2) tma_prefetch_desc(&tm.c2);
+    if (Tr::kNumOut == 2 && p.c2 != nullptr) tma_prefetch_desc(&tm.c2);
     if (Tr::kAux) tma_prefetch_desc(&tm.aux);
   }
   if (warp == 1 && elect_one()) {
@@ -202,12 +202,12 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
           if (Tr::kAux) stage64_read32(wb + 8192 + b * 2048, lane, aux);
           if (col < p.n) epi_compute<EPI>(p, row0 + lane, col, v, aux, o1, st);
           stage64_write32(wb + b * 2048, lane, v);
-          stage64_write32(wb + 4096 + b * 2048, lane, o1);
+          if (p.c2 != nullptr) stage64_write32(wb + 4096 + b * 2048, lane, o1);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm.c, wb + b * 2048, col, row0);  // boxes past N / M are clipped by the TMA unit
-            tma_store_2d(&tm.c2, wb + 4096 + b * 2048, col, row0);
+            if (p.c2 != nullptr) tma_store_2d(&tm.c2, wb + 4096 + b * 2048, col, row0);
             tma_store_commit();
           }
         }
@@ -263,7 +263,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             if (Tr::kAux) stage_read32(buf0, lane, half, aux);
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
-            if (Tr::kNumOut == 2) stage_write32(buf1, lane, half, o1);
+            if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
             if (Tr::kRedF32) {
               if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();
@@ -285,7 +285,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm.c, buf0, n0 + cl0, row0);
-            if (Tr::kNumOut == 2) tma_store_2d(&tm.c2, buf1, n0 + cl0, row0);
+            if (Tr::kNumOut == 2 && p.c2 != nullptr) tma_store_2d(&tm.c2, buf1, n0 + cl0, row0);
             tma_store_commit();
           }
         }

@@ -55,6 +55,15 @@ class Scratch:
         self._bufs.clear()
 
 
+def _fast_mode() -> bool:
+    """Activation policy. 'fast' (default) additionally keeps the two LayerNorm outputs and gelu(h) of every block
+    (16*d bf16 per token instead of 10*d: ~122 GB instead of ~76 GB at ViT-B-32 / batch 4096), which removes 48
+    LayerNorm recomputes per step and halves the HBM writes of the write-bound GELU-backward GEMM.
+    CLIPN_ACT_MODE=lean restores the recomputing schedule."""
+    import os
+    return os.environ.get("CLIPN_ACT_MODE", "fast") != "lean"
+
+
 @dataclass
 class BlockSaved:
     x_in: torch.Tensor
@@ -67,6 +76,9 @@ class BlockSaved:
     ln1_rstd: torch.Tensor
     ln2_mean: torch.Tensor
     ln2_rstd: torch.Tensor
+    h1: Optional[torch.Tensor] = None   # ln_1 output   (fast mode)
+    h2: Optional[torch.Tensor] = None   # ln_2 output   (fast mode)
+    g: Optional[torch.Tensor] = None    # gelu(h_pre)   (fast mode)
 
 
 @dataclass
@@ -83,8 +95,9 @@ def block_forward(P: Dict[str, torch.Tensor], pre: str, cfg: TowerCfg, x: torch.
                   save: bool) -> (torch.Tensor, Optional[BlockSaved]):
     M, d = x.shape
     dev = x.device
+    keep = save and _fast_mode()
     # ln_1 -> QKV (3 F.linear on in_proj chunks == one GEMM with N = 3d, transformer.py:195-197)
-    h1 = ws.get("h", (M, d), BF16, dev)
+    h1 = torch.empty((M, d), dtype=BF16, device=dev) if keep else ws.get("h", (M, d), BF16, dev)
     _, m1, r1 = ops.layernorm_fwd(x, P[pre + ".ln_1.weight"], P[pre + ".ln_1.bias"], out=h1, save_stats=save)
     qkv = torch.empty((M, 3 * d), dtype=BF16, device=dev) if save else ws.get("qkv", (M, 3 * d), BF16, dev)
     ops.gemm(h1, P[pre + ".attn.in_proj_weight"], bias=P[pre + ".attn.in_proj_bias"], out=qkv)
@@ -95,15 +108,16 @@ def block_forward(P: Dict[str, torch.Tensor], pre: str, cfg: TowerCfg, x: torch.
     ops.gemm(att, P[pre + ".attn.out_proj.weight"], bias=P[pre + ".attn.out_proj.bias"], aux=x,
              epilogue=L.EPI_BIAS_RESID, out=x_mid)
     # ln_2 -> c_fc + GELU -> c_proj + residual (transformer.py:295-299,329)
-    h2 = ws.get("h", (M, d), BF16, dev)
+    h2 = torch.empty((M, d), dtype=BF16, device=dev) if keep else ws.get("h", (M, d), BF16, dev)
     _, m2, r2 = ops.layernorm_fwd(x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=save)
     h_pre = torch.empty((M, 4 * d), dtype=BF16, device=dev) if save else ws.get("h_pre", (M, 4 * d), BF16, dev)
-    g = ws.get("g", (M, 4 * d), BF16, dev)
+    g = torch.empty((M, 4 * d), dtype=BF16, device=dev) if keep else ws.get("g", (M, 4 * d), BF16, dev)
     ops.gemm(h2, P[pre + ".mlp.c_fc.weight"], bias=P[pre + ".mlp.c_fc.bias"], epilogue=L.EPI_BIAS_GELU, out=h_pre, out2=g)
     x_out = torch.empty((M, d), dtype=BF16, device=dev)
     ops.gemm(g, P[pre + ".mlp.c_proj.weight"], bias=P[pre + ".mlp.c_proj.bias"], aux=x_mid, epilogue=L.EPI_BIAS_RESID,
              out=x_out)
-    saved = BlockSaved(x, qkv, att, x_mid, h_pre, lse, m1, r1, m2, r2) if save else None
+    saved = BlockSaved(x, qkv, att, x_mid, h_pre, lse, m1, r1, m2, r2, h1 if keep else None, h2 if keep else None,
+                       g if keep else None) if save else None
     return x_out, saved
 
 
@@ -120,13 +134,20 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     dev = dx_out.device
     # ---- MLP
     dh = ws.get("dh", (M, 4 * d), BF16, dev)
-    g = ws.get("g", (M, 4 * d), BF16, dev)
-    # dgrad of c_proj fused with GELU backward; also re-materialises g = gelu(h_pre)
-    ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g)
+    # dgrad of c_proj fused with GELU backward; re-materialises g = gelu(h_pre) unless the forward kept it
+    if s.g is not None:
+        g = s.g
+        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh)
+    else:
+        g = ws.get("g", (M, 4 * d), BF16, dev)
+        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g)
     _wgrad(dx_out, g, G[pre + ".mlp.c_proj.weight"])
     ops.colsum(dx_out, G[pre + ".mlp.c_proj.bias"])
-    h2 = ws.get("h", (M, d), BF16, dev)
-    ops.layernorm_fwd(s.x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=False)
+    if s.h2 is not None:
+        h2 = s.h2
+    else:
+        h2 = ws.get("h", (M, d), BF16, dev)
+        ops.layernorm_fwd(s.x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=False)
     _wgrad(dh, h2, G[pre + ".mlp.c_fc.weight"])
     ops.colsum(dh, G[pre + ".mlp.c_fc.bias"])
     dh2 = ws.get("dh_small", (M, d), BF16, dev)
@@ -141,8 +162,11 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     ops.colsum(dx_mid, G[pre + ".attn.out_proj.bias"])
     dqkv = ws.get("dqkv", (M, 3 * d), BF16, dev)
     ops.attention_bwd(s.qkv, s.att, datt, s.lse, batch, cfg.seq, cfg.heads, cfg.causal, out=dqkv)
-    h1 = ws.get("h", (M, d), BF16, dev)
-    ops.layernorm_fwd(s.x_in, P[pre + ".ln_1.weight"], P[pre + ".ln_1.bias"], out=h1, save_stats=False)
+    if s.h1 is not None:
+        h1 = s.h1
+    else:
+        h1 = ws.get("h", (M, d), BF16, dev)
+        ops.layernorm_fwd(s.x_in, P[pre + ".ln_1.weight"], P[pre + ".ln_1.bias"], out=h1, save_stats=False)
     _wgrad(dqkv, h1, G[pre + ".attn.in_proj_weight"])
     ops.colsum(dqkv, G[pre + ".attn.in_proj_bias"])
     dh1 = ws.get("dh_small", (M, d), BF16, dev)

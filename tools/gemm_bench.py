@@ -62,6 +62,15 @@ def main():
                        lambda: ops.gemm(dy, xx, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=gw, splits=s),
                        2.0 * M * gw.shape[0] * gw.shape[1])
         print(f"--- {tower}: one block's GEMMs {t:.3f} ms -> x12 = {12 * t:.1f} ms")
+        if os.environ.get("CLIPN_BENCH_DIAG"):
+            # epilogue / store-path diagnostics on the c_fc shape: one vs two outputs, with and without a mainloop
+            xs = x[:, :64].contiguous()
+            ws = wfc[:, :64].contiguous()
+            bench(f"{tower} DIAG fc shape STORE (1 output)", lambda: ops.gemm(x, wfc, bias=b4, out=o4), f(4 * d, d))
+            bench(f"{tower} DIAG fc shape GELU K=64", lambda: ops.gemm(xs, ws, bias=b4, epilogue=L.EPI_BIAS_GELU, out=o4, out2=o4b), f(4 * d, 64))
+            bench(f"{tower} DIAG fc shape STORE K=64", lambda: ops.gemm(xs, ws, bias=b4, out=o4), f(4 * d, 64))
+            bench(f"{tower} DIAG fc shape DGELU K=64", lambda: ops.gemm(xs, wpr[:64].contiguous(), b_mn=True, epilogue=L.EPI_DGELU, aux=x4, out=o4, out2=o4b), f(4 * d, 64))
+            bench(f"{tower} DIAG torch copy 2x[M,4d] (write-heavy HBM reference)", lambda: (o4.copy_(x4), o4b.copy_(x4)), 1.0)
         total += 12 * t
         del x, x4, x3, o3, o1, o4, o4b
     print(f"=== all tower GEMMs per step: {total:.1f} ms")
