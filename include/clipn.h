@@ -94,6 +94,9 @@ typedef struct clipn_gemm_desc {
      effective alpha = alpha * (*alpha_dev), effective logit_bias = logit_bias + (*logit_bias_dev) */
   const float* alpha_dev;
   const float* logit_bias_dev;
+  /* optional fp32 [N] accumulator: col_sum[n] += sum_m C[m,n] (bias gradient fused into the epilogue that
+     produces C; CLIPN_EPI_STORE and CLIPN_EPI_DGELU) */
+  float* col_sum;
 } clipn_gemm_desc;
 
 int clipn_gemm(const clipn_gemm_desc* d, clipn_stream_t stream);
@@ -117,8 +120,9 @@ int clipn_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
  * causal != 0 reproduces the additive -inf upper-triangular mask (transformer.py:1716-1722). */
 int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
                         int32_t causal, float scale, clipn_stream_t stream);
+/* dbias (optional, fp32 [3*H*64], +=): column sums of dqkv == gradient of in_proj_bias, fused into the kernel */
 int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                        int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
+                        float* dbias, int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
                         clipn_stream_t stream);
 
 /* ---- embeddings / pooling / normalize ----------------------------------------------------------- */

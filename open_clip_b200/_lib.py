@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ("logit_bias", C.c_float), ("gscale", C.c_float), ("col_w", C.c_float),
         ("label_offset", C.c_int32), ("negative_only", C.c_int32),
         ("alpha_dev", C.c_void_p), ("logit_bias_dev", C.c_void_p),
+        ("col_sum", C.c_void_p),
     ]
 
 
@@ -50,7 +51,7 @@ SIGNATURES = {
     "clipn_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
     "clipn_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "clipn_attention_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
-    "clipn_attention_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
+    "clipn_attention_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "clipn_patchify": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
     "clipn_vision_embed_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clipn_vision_embed_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P]),

@@ -103,6 +103,19 @@ __device__ __forceinline__ void store_tile16(const __nv_bfloat16* stage, __nv_bf
           *reinterpret_cast<const uint4*>(stage + r * LDS + v * 8);
   }
 }
+// dst[c] += sum over the 16 rows of a staged 16 x 64 bf16 tile (pad rows hold zeros): in_proj_bias gradient
+__device__ __forceinline__ void tile_colsum_atomic(const __nv_bfloat16* stage, float* dst, int lane) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 16; ++r) {
+    const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(stage + r * LDS + lane * 2);
+    const float2 f = __bfloat1622float2(v);
+    s0 += f.x;
+    s1 += f.y;
+  }
+  atomicAdd(dst + lane * 2, s0);
+  atomicAdd(dst + lane * 2 + 1, s1);
+}
 __device__ __forceinline__ void stage_frag_tile(__nv_bfloat16* stage, const float (&o)[8][4], float s0, float s1,
                                                 int lane) {
   const int r = lane >> 2;
@@ -442,8 +455,8 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 template <int NT>
 __global__ void __launch_bounds__(160, 2)
 attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                           const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv, int items, int seq,
-                           int heads, int causal, float scale) {
+                           const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv,
+                           float* __restrict__ dbias, int items, int seq, int heads, int causal, float scale) {
   extern __shared__ __align__(16) uint8_t smem_att[];
   constexpr int Lp = NT * 8;    // 64 or 80
   constexpr int LDP = Lp + 8;   // pitch of the P / dS tiles (bf16): conflict-free ldmatrix rows
@@ -540,6 +553,7 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       stage_frag_tile(sOut, dq, scale, scale, lane);
       __syncwarp();
       store_tile16(sOut, dq_base, ld, r0, seq, lane);
+      if (dbias != nullptr) tile_colsum_atomic(sOut, dbias + h * HD, lane);
     }
     __syncthreads();
 
@@ -564,10 +578,12 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       stage_frag_tile(sOut, dk, scale, scale, lane);
       __syncwarp();
       store_tile16(sOut, dq_base + d, ld, c0, seq, lane);
+      if (dbias != nullptr) tile_colsum_atomic(sOut, dbias + d + h * HD, lane);
       __syncwarp();
       stage_frag_tile(sOut, dv, 1.f, 1.f, lane);
       __syncwarp();
       store_tile16(sOut, dq_base + 2 * d, ld, c0, seq, lane);
+      if (dbias != nullptr) tile_colsum_atomic(sOut, dbias + 2 * d + h * HD, lane);
     }
     __syncthreads();  // tiles, sP/sdS and sLse are rewritten by the next item
   }
@@ -617,7 +633,7 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
 }
 
 extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                                   int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
+                                   float* dbias, int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
                                    clipn_stream_t stream) {
   (void)out;  // D = rowsum(dO o O) is recomputed as sum_j P_ij dP_ij: the forward output is not re-read
   CLIPN_REQUIRE(qkv && dout && lse && dqkv, "attention_bwd: null pointer");
@@ -643,14 +659,14 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
       CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attention_bwd_small_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                                  reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads,
-                                                                 causal, scale);
+                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, items, seq,
+                                                                 heads, causal, scale);
     } else {
       CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       attention_bwd_small_kernel<10><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                                   reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-                                                                  reinterpret_cast<__nv_bfloat16*>(dqkv), items, seq, heads,
-                                                                  causal, scale);
+                                                                  reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, items, seq,
+                                                                  heads, causal, scale);
     }
     CLIPN_CHECK_CUDA(cudaGetLastError());
     return CLIPN_OK;
@@ -681,5 +697,9 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
                                                          scale, nst);
   }
   CLIPN_CHECK_CUDA(cudaGetLastError());
+  // the general (long-sequence) kernel does not fuse the in_proj_bias gradient: one extra pass over dqkv
+  if (dbias != nullptr)
+    return clipn_colsum(dqkv, 3 * static_cast<int64_t>(heads) * HD, dbias, static_cast<int64_t>(batch) * seq,
+                        3 * heads * HD, stream);
   return CLIPN_OK;
 }

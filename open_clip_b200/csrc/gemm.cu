@@ -117,6 +117,28 @@ __device__ __forceinline__ void load_bias32(const void* bias, int col, float (&b
   }
 }
 
+// Bias gradient fused into the epilogue: col_sum[col + l] += sum over this warp's 32 rows of v[l].
+// Register transpose-reduce: at step `off` a lane keeps the half of its column range selected by its own bit
+// `off` and receives the partner's partial sums for it; after 5 steps lane l holds column l's total
+// (31 shuffles + 31 adds per 32x32 piece).  Warp-convergent; destroys v.
+__device__ __forceinline__ void epi_col_sum(const GemmParams& p, int row, int col, float (&v)[32]) {
+  const int lane = lane_id();
+  const bool row_ok = row < p.m;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = row_ok ? v[i] : 0.f;
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  if (col + lane < p.n) atomicAdd(p.col_sum + col + lane, v[0]);
+}
+
 // Staging tile access: row r (0..31) of a 1024-aligned 32x128B SW128 tile, 16-byte chunk c (0..7).
 __device__ __forceinline__ uint4* stage_chunk(uint8_t* buf, int r, int c) {
   return reinterpret_cast<uint4*>(buf + r * 128 + ((c ^ (r & 7)) << 4));
@@ -453,6 +475,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
             if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
+            if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr)
+              epi_col_sum(p, row, n0 + cl, v);
             if (Tr::kRedF32) {
               // fp32 32x32 tile -> swizzled staging -> cp.reduce.async.bulk.tensor (.add) into C
               if (lane == 0) tma_store_wait_read<0>();
@@ -575,6 +599,7 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
       if (store_c) store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
       if (Tr::kNumOut == 2 && p.c2 != nullptr) store_bf16_row32(p.c2, p.ldc2, row, col, o1, nvalid);
     }
+    if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr) epi_col_sum(p, row, col, v);
   }
   epi_finish<EPI>(p, row, slab, st);
 }
@@ -691,6 +716,9 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   p.scalar_acc = d.scalar_acc; p.logit_bias = d.logit_bias; p.gscale = d.gscale; p.col_w = d.col_w;
   p.label_offset = d.label_offset; p.negative_only = d.negative_only;
   p.alpha_dev = d.alpha_dev; p.logit_bias_dev = d.logit_bias_dev;
+  p.col_sum = d.col_sum;
+  if (d.col_sum != nullptr)
+    CLIPN_REQUIRE(ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_DGELU, "gemm: col_sum only with STORE / DGELU epilogues");
 
   if (use_ref) {
     RefOperands ops;

@@ -27,6 +27,7 @@ struct GemmParams {
   float logit_bias, gscale, col_w;
   int label_offset, negative_only;
   const float* alpha_dev; const float* logit_bias_dev;
+  float* col_sum;
 };
 
 struct RefOperands {

@@ -203,6 +203,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
           if (col < p.n) epi_compute<EPI>(p, row0 + lane, col, v, aux, o1, st);
           stage64_write32(wb + b * 2048, lane, v);
           if (p.c2 != nullptr) stage64_write32(wb + 4096 + b * 2048, lane, o1);
+          if (EPI == CLIPN_EPI_DGELU && p.col_sum != nullptr && col < p.n) epi_col_sum(p, row0 + lane, col, v);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
@@ -264,6 +265,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
             if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
+            if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr)
+              epi_col_sum(p, row, n0 + cl, v);
             if (Tr::kRedF32) {
               if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();

@@ -18,8 +18,8 @@ F32 = torch.float32
 
 # instrumentation used by bench.py: kernel-launch counter and CUDA events around one GEMM signature
 LAUNCHES = 0
-PROFILE_KEY = None          # (M, N, K, epilogue) or None
-PROFILE_EVENTS = []         # [(start_event, end_event)] recorded on the launching stream
+PROFILE_KEY = None          # (M, N, K, epilogue), "all", or None
+PROFILE_EVENTS = []         # [(start_event, end_event, (M, N, K, epilogue, a_mn, b_mn))] on the launching stream
 
 
 def _call(rc: int, n: int = 1) -> None:
@@ -82,12 +82,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     for k, v in extra.items():
         setattr(d, k, v.data_ptr() if isinstance(v, torch.Tensor) else v)
     fn = L.lib().clipn_gemm_ref if ref else L.lib().clipn_gemm
-    if PROFILE_KEY is not None and PROFILE_KEY == (M, N, K, epilogue):
+    if PROFILE_KEY is not None and (PROFILE_KEY == "all" or PROFILE_KEY == (M, N, K, epilogue)):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _call(fn(C.byref(d), _stream()))
         e1.record()
-        PROFILE_EVENTS.append((e0, e1))
+        PROFILE_EVENTS.append((e0, e1, (M, N, K, epilogue, bool(a_mn), bool(b_mn))))
     else:
         _call(fn(C.byref(d), _stream()))
     return out
@@ -141,11 +141,14 @@ def attention_fwd(qkv, batch, seq, heads, causal, out=None):
     return o, lse
 
 
-def attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, out=None):
+def attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, out=None, dbias=None):
+    """dbias (fp32 [3d], +=): in_proj_bias gradient = column sums of dqkv, fused into the kernel."""
     _chk(qkv, BF16, "attnb.qkv"); _chk(o, BF16, "attnb.o"); _chk(do, BF16, "attnb.do"); _chk(lse, F32, "attnb.lse")
     dqkv = out if out is not None else torch.empty_like(qkv)
+    if dbias is not None:
+        _chk(dbias, F32, "attnb.dbias")
     _call(L.lib().clipn_attention_bwd(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                        batch, seq, heads, int(causal), 64 ** -0.5, _stream()))
+                                        _ptr(dbias), batch, seq, heads, int(causal), 64 ** -0.5, _stream()))
     return dqkv
 
 

@@ -135,12 +135,15 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     # ---- MLP
     dh = ws.get("dh", (M, 4 * d), BF16, dev)
     # dgrad of c_proj fused with GELU backward; re-materialises g = gelu(h_pre) unless the forward kept it
+    # (the c_fc bias gradient = column sums of dh is accumulated by the same epilogue)
     if s.g is not None:
         g = s.g
-        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh)
+        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh,
+                 col_sum=G[pre + ".mlp.c_fc.bias"])
     else:
         g = ws.get("g", (M, 4 * d), BF16, dev)
-        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g)
+        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g,
+                 col_sum=G[pre + ".mlp.c_fc.bias"])
     _wgrad(dx_out, g, G[pre + ".mlp.c_proj.weight"])
     ops.colsum(dx_out, G[pre + ".mlp.c_proj.bias"])
     if s.h2 is not None:
@@ -149,7 +152,6 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
         h2 = ws.get("h", (M, d), BF16, dev)
         ops.layernorm_fwd(s.x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=False)
     _wgrad(dh, h2, G[pre + ".mlp.c_fc.weight"])
-    ops.colsum(dh, G[pre + ".mlp.c_fc.bias"])
     dh2 = ws.get("dh_small", (M, d), BF16, dev)
     ops.gemm(dh, P[pre + ".mlp.c_fc.weight"], b_mn=True, out=dh2)
     dx_mid = ws.get("dx_mid", (M, d), BF16, dev)
@@ -161,14 +163,14 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     _wgrad(dx_mid, s.att, G[pre + ".attn.out_proj.weight"])
     ops.colsum(dx_mid, G[pre + ".attn.out_proj.bias"])
     dqkv = ws.get("dqkv", (M, 3 * d), BF16, dev)
-    ops.attention_bwd(s.qkv, s.att, datt, s.lse, batch, cfg.seq, cfg.heads, cfg.causal, out=dqkv)
+    ops.attention_bwd(s.qkv, s.att, datt, s.lse, batch, cfg.seq, cfg.heads, cfg.causal, out=dqkv,
+                      dbias=G[pre + ".attn.in_proj_bias"])
     if s.h1 is not None:
         h1 = s.h1
     else:
         h1 = ws.get("h", (M, d), BF16, dev)
         ops.layernorm_fwd(s.x_in, P[pre + ".ln_1.weight"], P[pre + ".ln_1.bias"], out=h1, save_stats=False)
     _wgrad(dqkv, h1, G[pre + ".attn.in_proj_weight"])
-    ops.colsum(dqkv, G[pre + ".attn.in_proj_bias"])
     dh1 = ws.get("dh_small", (M, d), BF16, dev)
     ops.gemm(dqkv, P[pre + ".attn.in_proj_weight"], b_mn=True, out=dh1)
     dx_in = torch.empty((M, d), dtype=BF16, device=dev)

@@ -26,7 +26,11 @@ def test_attention_fwd_bwd(batch, seq, heads, causal):
         s = s + mask
     assert rel_err(lse, torch.logsumexp(s, -1)) < 1e-4
     do = randn(batch * seq, d, seed=seq + 1)
-    dqkv = ops.attention_bwd(qkv, o, do, lse, batch, seq, heads, causal)
+    dbias = torch.zeros(3 * d, dtype=torch.float32, device="cuda")
+    dqkv = ops.attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, dbias=dbias)
+    # fused in_proj_bias gradient == column sums of the (bf16) dqkv the kernel wrote
+    want = dqkv.float().sum(0)
+    assert float((dbias - want).norm() / (want.norm() + 1e-6 * dqkv.float().norm())) < 2e-3
     ref_flat.backward(do.float())
     got = dqkv.float().view(batch, seq, 3, heads, 64)
     for i, name in enumerate("qkv"):

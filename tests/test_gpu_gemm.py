@@ -72,12 +72,20 @@ def test_dgelu(shape):
     hpre = randn(M, N, seed=8)
     dh = torch.empty((M, N), dtype=BF16, device="cuda")
     g = torch.empty((M, N), dtype=BF16, device="cuda")
-    ops.gemm(A, Bm, b_mn=True, epilogue=L.EPI_DGELU, aux=hpre, out=dh, out2=g)
+    csum = torch.zeros(N, dtype=F32, device="cuda")
+    ops.gemm(A, Bm, b_mn=True, epilogue=L.EPI_DGELU, aux=hpre, out=dh, out2=g, col_sum=csum)
     x = hpre.float().requires_grad_(True)
     y = torch.nn.functional.gelu(x)
     y.backward(ref)
     assert rel_err(dh, x.grad) < 6e-3
     assert rel_err(g, y.detach()) < 4e-3
+    assert rel_err(csum, x.grad.sum(0)) < 2e-3       # fused bias gradient (column sums of dh)
+    dh2 = torch.empty_like(dh)                       # second output is optional
+    ops.gemm(A, Bm, b_mn=True, epilogue=L.EPI_DGELU, aux=hpre, out=dh2)
+    assert torch.equal(dh, dh2)
+    csum2 = torch.zeros(N, dtype=F32, device="cuda")
+    st = ops.gemm(A, Bm, b_mn=True, col_sum=csum2)   # STORE + fused column sums
+    assert rel_err(csum2, ref.sum(0)) < 2e-3 and rel_err(st, ref) < 4e-3
 
 
 @pytest.mark.parametrize("splits", [1, 3, 7])
