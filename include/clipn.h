@@ -66,6 +66,10 @@ enum clipn_epilogue {
                                also accumulates d(loss)/d(logit_scale) (ClipLoss bwd)                     */
   CLIPN_EPI_SIGLIP = 8,     /* softplus / sigmoid epilogue for SigLipLoss (loss.py:351-367): see
                                clipn_siglip_* below                                                       */
+  CLIPN_EPI_BIAS_GELU_GRAD = 9, /* t = bf16(acc + bias); C = bf16(gelu'(t)); C2 = bf16(gelu_erf(t)): the forward
+                               keeps the GELU derivative instead of the pre-activation, so the backward epilogue
+                               is a plain multiply (CLIPN_EPI_MUL_AUX) instead of erf + exp per element          */
+  CLIPN_EPI_MUL_AUX = 10,   /* C = bf16(acc * aux[m,n])   (c_proj dgrad x saved gelu'(h); optional col_sum)      */
 };
 
 typedef struct clipn_gemm_desc {

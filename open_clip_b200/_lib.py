@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libclipn.so")
 
 EPI_STORE, EPI_BIAS_GELU, EPI_BIAS_RESID, EPI_DGELU, EPI_ACCUM_F32, EPI_STORE_F32, EPI_LSE, EPI_CLIP_DLOGITS, \
-    EPI_SIGLIP = range(9)
+    EPI_SIGLIP, EPI_BIAS_GELU_GRAD, EPI_MUL_AUX = range(11)
 
 
 class GemmDesc(C.Structure):

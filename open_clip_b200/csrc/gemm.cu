@@ -36,9 +36,12 @@ constexpr float kLog2e = 1.4426950408889634f;
 template <int EPI>
 struct EpiTraits {
   static constexpr bool kOutTma = EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_BIAS_GELU || EPI == CLIPN_EPI_BIAS_RESID ||
-                                  EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_CLIP_DLOGITS || EPI == CLIPN_EPI_SIGLIP;
-  static constexpr int kNumOut = (EPI == CLIPN_EPI_BIAS_GELU || EPI == CLIPN_EPI_DGELU) ? 2 : 1;
-  static constexpr bool kAux = EPI == CLIPN_EPI_BIAS_RESID || EPI == CLIPN_EPI_DGELU;
+                                  EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_CLIP_DLOGITS || EPI == CLIPN_EPI_SIGLIP ||
+                                  EPI == CLIPN_EPI_BIAS_GELU_GRAD || EPI == CLIPN_EPI_MUL_AUX;
+  static constexpr int kNumOut =
+      (EPI == CLIPN_EPI_BIAS_GELU || EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_BIAS_GELU_GRAD) ? 2 : 1;
+  static constexpr bool kAux = EPI == CLIPN_EPI_BIAS_RESID || EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_MUL_AUX;
+  static constexpr bool kColSum = EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU || EPI == CLIPN_EPI_MUL_AUX;
   static constexpr bool kRedF32 = EPI == CLIPN_EPI_ACCUM_F32;  // fp32 tile reduce-added by TMA (cp.reduce.async.bulk)
   static constexpr int kBufs = kOutTma ? kNumOut : (kRedF32 ? 1 : 0);
 };
@@ -195,6 +198,17 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
       v[i] = bf16_round(v[i] + b[i]);
       o1[i] = gelu_exact(v[i]);
     }
+  } else if constexpr (EPI == CLIPN_EPI_BIAS_GELU_GRAD) {
+    float b[32];
+    load_bias32(p.bias, col, b, nvalid);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float t = bf16_round(v[i] + b[i]);
+      gelu_and_grad(t, o1[i], v[i]);  // C2 = gelu(t), C = gelu'(t)
+    }
+  } else if constexpr (EPI == CLIPN_EPI_MUL_AUX) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= aux[i];
   } else if constexpr (EPI == CLIPN_EPI_BIAS_RESID) {
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
@@ -475,7 +489,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
             if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
-            if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr)
+            if (Tr::kColSum && p.col_sum != nullptr)
               epi_col_sum(p, row, n0 + cl, v);
             if (Tr::kRedF32) {
               // fp32 32x32 tile -> swizzled staging -> cp.reduce.async.bulk.tensor (.add) into C
@@ -599,7 +613,7 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
       if (store_c) store_bf16_row32(p.c, p.ldc, row, col, v, nvalid);
       if (Tr::kNumOut == 2 && p.c2 != nullptr) store_bf16_row32(p.c2, p.ldc2, row, col, o1, nvalid);
     }
-    if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr) epi_col_sum(p, row, col, v);
+    if (Tr::kColSum && p.col_sum != nullptr) epi_col_sum(p, row, col, v);
   }
   epi_finish<EPI>(p, row, slab, st);
 }
@@ -672,6 +686,8 @@ static int launch_ref(const GemmParams& p, const RefOperands& ops, int bn, cudaS
     case CLIPN_EPI_LSE: MACRO(CLIPN_EPI_LSE); break;                       \
     case CLIPN_EPI_CLIP_DLOGITS: MACRO(CLIPN_EPI_CLIP_DLOGITS); break;     \
     case CLIPN_EPI_SIGLIP: MACRO(CLIPN_EPI_SIGLIP); break;                 \
+    case CLIPN_EPI_BIAS_GELU_GRAD: MACRO(CLIPN_EPI_BIAS_GELU_GRAD); break; \
+    case CLIPN_EPI_MUL_AUX: MACRO(CLIPN_EPI_MUL_AUX); break;               \
     default: return set_error_arg("unknown epilogue", __FILE__, __LINE__); \
   }
 
@@ -685,11 +701,13 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   const int ep = d.epilogue;
   const bool needs_c = !(ep == CLIPN_EPI_LSE || (ep == CLIPN_EPI_SIGLIP && d.c == nullptr));
   if (needs_c) CLIPN_REQUIRE(d.c != nullptr && d.ldc % 8 == 0, "gemm: C missing or ldc not a multiple of 8");
-  if (ep == CLIPN_EPI_BIAS_GELU) CLIPN_REQUIRE(d.c2 != nullptr, "gemm: C2 required");
+  const bool two_out = ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_BIAS_GELU_GRAD;
+  const bool has_aux = ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_MUL_AUX;
+  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_GELU_GRAD) CLIPN_REQUIRE(d.c2 != nullptr, "gemm: C2 required");
   if (d.c2 != nullptr) CLIPN_REQUIRE(d.ldc2 % 8 == 0, "gemm: ldc2 must be a multiple of 8");  // DGELU: C2 optional
-  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID) CLIPN_REQUIRE(d.bias != nullptr, "gemm: bias required");
-  if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU)
-    CLIPN_REQUIRE(d.aux != nullptr && d.ldaux % 8 == 0, "gemm: aux required");
+  if (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_BIAS_GELU_GRAD)
+    CLIPN_REQUIRE(d.bias != nullptr, "gemm: bias required");
+  if (has_aux) CLIPN_REQUIRE(d.aux != nullptr && d.ldaux % 8 == 0, "gemm: aux required");
   if (ep == CLIPN_EPI_LSE) CLIPN_REQUIRE(d.part_max && d.part_sum && d.pos, "gemm: LSE buffers required");
   if (ep == CLIPN_EPI_CLIP_DLOGITS) CLIPN_REQUIRE(d.row_lse && (d.col_w == 0.f || d.col_lse), "gemm: lse vectors");
 
@@ -718,7 +736,8 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   p.alpha_dev = d.alpha_dev; p.logit_bias_dev = d.logit_bias_dev;
   p.col_sum = d.col_sum;
   if (d.col_sum != nullptr)
-    CLIPN_REQUIRE(ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_DGELU, "gemm: col_sum only with STORE / DGELU epilogues");
+    CLIPN_REQUIRE(ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_MUL_AUX,
+                  "gemm: col_sum only with STORE / DGELU / MUL_AUX epilogues");
 
   if (use_ref) {
     RefOperands ops;
@@ -760,9 +779,10 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
   }
   // epilogue staging maps: 64-column x 32-row bf16 boxes (one warp's tile), SW128
   const bool out_tma = ep == CLIPN_EPI_STORE || ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_BIAS_RESID ||
-                       ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_CLIP_DLOGITS || (ep == CLIPN_EPI_SIGLIP && d.c != nullptr);
+                       ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_CLIP_DLOGITS || (ep == CLIPN_EPI_SIGLIP && d.c != nullptr) ||
+                       ep == CLIPN_EPI_BIAS_GELU_GRAD || ep == CLIPN_EPI_MUL_AUX;
   // pair kernel + two-output epilogue: 32-column pieces (64-byte rows, SW64), see TileCfg::kPipedEpi
-  const bool piped = use_pair && (ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU);
+  const bool piped = use_pair && two_out;
   const uint32_t ebox = piped ? 32 : 64;
   const int esw = piped ? 64 : 128;
   if (out_tma) {
@@ -773,11 +793,11 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
     rc = make_tmap_2d(&tm.c, d.c, 4, d.n, d.m, d.ldc * 4, 32, 32, 128);
     if (rc) return rc;
   }
-  if ((ep == CLIPN_EPI_BIAS_GELU || ep == CLIPN_EPI_DGELU) && d.c2 != nullptr) {
+  if (two_out && d.c2 != nullptr) {
     rc = make_tmap_2d(&tm.c2, d.c2, 2, d.n, d.m, d.ldc2 * 2, ebox, 32, esw);
     if (rc) return rc;
   }
-  if (ep == CLIPN_EPI_BIAS_RESID || ep == CLIPN_EPI_DGELU) {
+  if (has_aux) {
     rc = make_tmap_2d(&tm.aux, d.aux, 2, d.n, d.m, d.ldaux * 2, ebox, 32, esw);
     if (rc) return rc;
   }

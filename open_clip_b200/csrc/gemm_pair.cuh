@@ -265,7 +265,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
             epi_compute<EPI>(p, row, n0 + cl, v, aux, o1, st);
             if (store_c) stage_write32(buf0, lane, half, v);
             if (Tr::kNumOut == 2 && p.c2 != nullptr) stage_write32(buf1, lane, half, o1);
-            if ((EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_DGELU) && p.col_sum != nullptr)
+            if (Tr::kColSum && p.col_sum != nullptr)
               epi_col_sum(p, row, n0 + cl, v);
             if (Tr::kRedF32) {
               if (lane == 0) tma_store_wait_read<0>();

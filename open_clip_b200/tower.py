@@ -112,7 +112,10 @@ def block_forward(P: Dict[str, torch.Tensor], pre: str, cfg: TowerCfg, x: torch.
     _, m2, r2 = ops.layernorm_fwd(x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=save)
     h_pre = torch.empty((M, 4 * d), dtype=BF16, device=dev) if save else ws.get("h_pre", (M, 4 * d), BF16, dev)
     g = torch.empty((M, 4 * d), dtype=BF16, device=dev) if keep else ws.get("g", (M, 4 * d), BF16, dev)
-    ops.gemm(h2, P[pre + ".mlp.c_fc.weight"], bias=P[pre + ".mlp.c_fc.bias"], epilogue=L.EPI_BIAS_GELU, out=h_pre, out2=g)
+    # fast mode keeps gelu'(h) in the `h_pre` slot (and gelu(h)), so the backward epilogue is a plain multiply;
+    # lean mode keeps the pre-activation h and re-derives both in the backward (CLIPN_EPI_DGELU)
+    ops.gemm(h2, P[pre + ".mlp.c_fc.weight"], bias=P[pre + ".mlp.c_fc.bias"],
+             epilogue=L.EPI_BIAS_GELU_GRAD if keep else L.EPI_BIAS_GELU, out=h_pre, out2=g)
     x_out = torch.empty((M, d), dtype=BF16, device=dev)
     ops.gemm(g, P[pre + ".mlp.c_proj.weight"], bias=P[pre + ".mlp.c_proj.bias"], aux=x_mid, epilogue=L.EPI_BIAS_RESID,
              out=x_out)
@@ -138,8 +141,8 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     # (the c_fc bias gradient = column sums of dh is accumulated by the same epilogue)
     if s.g is not None:
         g = s.g
-        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh,
-                 col_sum=G[pre + ".mlp.c_fc.bias"])
+        ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_MUL_AUX, aux=s.h_pre, out=dh,
+                 col_sum=G[pre + ".mlp.c_fc.bias"])  # s.h_pre holds gelu'(h) in fast mode
     else:
         g = ws.get("g", (M, 4 * d), BF16, dev)
         ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g,

@@ -88,6 +88,27 @@ def test_dgelu(shape):
     assert rel_err(csum2, ref.sum(0)) < 2e-3 and rel_err(st, ref) < 4e-3
 
 
+@pytest.mark.parametrize("shape", SHAPES[1:5])
+def test_gelu_grad_forward_and_mul_aux_backward(shape):
+    """fast-mode MLP pair: forward keeps gelu'(h) and gelu(h); backward multiplies the dgrad by the saved derivative."""
+    M, N, K = shape
+    A, Bm, ref = _operands(M, N, K, False, False, 5)
+    bias = randn(N, seed=6)
+    gp = torch.empty((M, N), dtype=BF16, device="cuda")
+    g = torch.empty((M, N), dtype=BF16, device="cuda")
+    ops.gemm(A, Bm, bias=bias, epilogue=L.EPI_BIAS_GELU_GRAD, out=gp, out2=g)
+    h = (ref + bias.float()).to(BF16).float().requires_grad_(True)
+    y = torch.nn.functional.gelu(h)
+    y.sum().backward()
+    assert rel_err(g, y.detach()) < 6e-3
+    assert rel_err(gp, h.grad) < 6e-3
+    csum = torch.zeros(N, dtype=F32, device="cuda")
+    dh = ops.gemm(A, Bm, epilogue=L.EPI_MUL_AUX, aux=gp, col_sum=csum)
+    want = ref * gp.float()
+    assert rel_err(dh, want) < 4e-3
+    assert rel_err(csum, want.sum(0)) < 2e-3
+
+
 @pytest.mark.parametrize("splits", [1, 3, 7])
 @pytest.mark.parametrize("shape", [(256, 128, 4096), (768, 768, 6400), (2304, 768, 3200)])
 def test_wgrad_split_k(shape, splits):

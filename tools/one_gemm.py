@@ -1,11 +1,22 @@
+"""Launch one GEMM signature a few times (for ncu captures): python tools/one_gemm.py {proj|dgelu|gelu}"""
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
 from open_clip_b200 import ops, _lib as L
+which = sys.argv[1] if len(sys.argv) > 1 else "proj"
 M, d = 51200, 768
-x4 = torch.randn(M, 4*d, device="cuda").to(torch.bfloat16)
-x = torch.randn(M, d, device="cuda").to(torch.bfloat16)
-w = (torch.randn(d, 4*d, device="cuda")*0.02).to(torch.bfloat16)
-o = torch.empty_like(x)
+bf = torch.bfloat16
+x = torch.randn(M, d, device="cuda").to(bf)
+x4 = torch.randn(M, 4 * d, device="cuda").to(bf)
+o4, o4b, o1 = torch.empty_like(x4), torch.empty_like(x4), torch.empty_like(x)
+wfc = (torch.randn(4 * d, d, device="cuda") * 0.02).to(bf)
+wpr = (torch.randn(d, 4 * d, device="cuda") * 0.02).to(bf)
+b4 = torch.zeros(4 * d, device="cuda", dtype=bf)
+cs = torch.zeros(4 * d, device="cuda")
 for _ in range(3):
-    ops.gemm(x4, w, out=o)
+    if which == "proj":
+        ops.gemm(x4, wpr, out=o1)
+    elif which == "dgelu":
+        ops.gemm(x, wpr, b_mn=True, epilogue=L.EPI_DGELU, aux=x4, out=o4, col_sum=cs)
+    elif which == "gelu":
+        ops.gemm(x, wfc, bias=b4, epilogue=L.EPI_BIAS_GELU, out=o4, out2=o4b)
 torch.cuda.synchronize()
