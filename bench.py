@@ -302,7 +302,7 @@ def main():
 
     if rank == 0:
         epi_names = ["STORE", "BIAS_GELU", "BIAS_RESID", "DGELU", "ACCUM_F32(split-K wgrad)", "STORE_F32", "LSE",
-                     "CLIP_DLOGITS", "SIGLIP"]
+                     "CLIP_DLOGITS", "SIGLIP", "BIAS_GELU_GRAD", "MUL_AUX"]
         fam_flops = sum(2.0 * s[0] * s[1] * s[2] * sig_count[s] for s in sig_time)
         fam_ms = sum(sig_time.values())
         top = max(sig_time, key=sig_time.get) if sig_time else None
