@@ -313,6 +313,12 @@ def main():
         gemm_ms = [0] * (sig_count[top] if top else 0)
         top_name = ("gemm_tc2_kernel<256,%s> M=%d N=%d K=%d%s" % (epi_names[top[3]], top[0], top[1], top[2],
                     " (MN-major operands)" if top[4] else "")) if top else "n/a"
+        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r01_ncu_pair_gelu.txt,
+        # r01_ncu_pair_dgelu.txt: dram__bytes_read.sum + dram__bytes_write.sum at M = 51200), scaled linearly in M
+        ncu_traffic_m51200 = {(1, 3072, 768): 658.25e6, (9, 3072, 768): 658.25e6, (3, 3072, 768): 679.6e6}
+        traffic = None
+        if top and (top[3], top[1], top[2]) in ncu_traffic_m51200:
+            traffic = ncu_traffic_m51200[(top[3], top[1], top[2])] * top[0] / 51200.0
         out = {
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -324,7 +330,9 @@ def main():
             "roofline": {"bound": "tensor", "kernel": top_name,
                          "share_of_step": (sig_time[top] / args.steps) / ms_step if top else None,
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
+                         "algorithmic_bytes": (2.0 * (top[0] * top[2] + top[1] * top[2]) +
+                                               2.0 * top[0] * top[1] * (2 if top[3] in (1, 9) else 1)) if top else None,
                          "launches_timed": len(gemm_ms), "avg_launch_ms": avg_ms,
                          "flops_per_launch": flops_launch, "peak_source": peaks["source"] + ", sustained"},
             "roofline_gemm_family": {"bound": "tensor", "achieved": fam_flops / (fam_ms * 1e-3) / 1e12 if fam_ms else None,
