@@ -293,10 +293,21 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float (&f)[8]) {
 // three orders of magnitude below the bf16 rounding of the result).  e^{-z^2} with z = x/sqrt(2) is also the
 // Gaussian the derivative needs, so the backward costs two more FMAs.  ~18 issue slots per element instead of ~60
 // for erff() + expf(): the GELU epilogues were issue-bound, not tensor-bound (profiles/ round 1).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// 8 FFMA + 5 FMUL + 2 MUFU + 1 LOP per element for gelu AND its derivative (raw MUFU ops: the range-checked
+// exp2f()/__fdividef() wrappers cost 3 FSETP/FSEL + 3 FMUL more per element, and the GELU epilogues are issue-bound).
 __device__ __forceinline__ void gelu_core(float x, float& half_one_plus_erf, float& gauss) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  gauss = exp2f(-z * z * 1.4426950408889634f);  // e^{-x^2/2}
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));  // 1/(1 + p|x|/sqrt2), arg in [1, inf)
+  gauss = ex2_approx(x * x * -0.72134752044448170f);                                     // e^{-x^2/2}
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
