@@ -97,12 +97,10 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 4 : 3) layernorm_fwd_kernel(
 
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward.  dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += sum dy*xhat,
-// dbeta += sum dy.  Optional residual-gradient add fused into the store.  x and dy of the NEXT row are
-// prefetched (packed bf16 registers) while the current row is processed; the current row stays packed and is
-// unpacked twice (statistics pass, output pass) so the prefetch fits the register budget.
+// dbeta += sum dy.  Optional residual-gradient add fused into the store.
 // ------------------------------------------------------------------------------------------------
 template <int NCH>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+__global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                             const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in,
@@ -124,40 +122,29 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_dg[c][j] = acc_db[c][j] = 0.f;
 
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * wpb;
-  int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5);
-  uint4 cx[NCH], cdy[NCH], nx[NCH], ndy[NCH];
-  auto load_row = [&](int64_t r, uint4(&dx_)[NCH], uint4(&ddy)[NCH]) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + r * d);
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * d);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      const int ci = lane + c * 32;
-      dx_[c] = (ci < nchunk) ? xr[ci] : make_uint4(0, 0, 0, 0);
-      ddy[c] = (ci < nchunk) ? dyr[ci] : make_uint4(0, 0, 0, 0);
-    }
-  };
-  if (row < rows) load_row(row, cx, cdy);
-  for (; row < rows; row += stride) {
-    if (row + stride < rows) load_row(row + stride, nx, ndy);
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * d);
     const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NCH][8], g[NCH][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float xv[8], dv[8];
-        unpack_bf16x8(cx[c], xv);
-        unpack_bf16x8(cdy[c], dv);
+        unpack_bf16x8(xr[ci], xv);
+        unpack_bf16x8(dyr[ci], dv);
         const float4 g0 = reinterpret_cast<const float4*>(gamma)[ci * 2], g1 = reinterpret_cast<const float4*>(gamma)[ci * 2 + 1];
         const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float xh = (xv[j] - mean) * rstd;
-          const float g = dv[j] * gm[j];
-          s1 += g;
-          s2 += g * xh;
-          acc_dg[c][j] += dv[j] * xh;
+          xh[c][j] = (xv[j] - mean) * rstd;
+          g[c][j] = dv[j] * gm[j];
+          s1 += g[c][j];
+          s2 += g[c][j] * xh[c][j];
+          acc_dg[c][j] += dv[j] * xh[c][j];
           acc_db[c][j] += dv[j];
         }
       }
@@ -170,13 +157,9 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
     for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
-        float xv[8], dv[8], o[8];
-        unpack_bf16x8(cx[c], xv);
-        unpack_bf16x8(cdy[c], dv);
-        const float4 g0 = reinterpret_cast<const float4*>(gamma)[ci * 2], g1 = reinterpret_cast<const float4*>(gamma)[ci * 2 + 1];
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2);
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
         if (rr) {
           float r[8];
           unpack_bf16x8(rr[ci], r);
@@ -185,11 +168,6 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const __nv_bfloat
         }
         dxr[ci] = pack_bf16x8(o);
       }
-    }
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      cx[c] = nx[c];
-      cdy[c] = ndy[c];
     }
   }
   // block reduce of the per-lane column partials, then one atomic per column per block
@@ -546,7 +524,7 @@ extern "C" int clipn_layernorm_bwd(const void* dy, const void* x, const float* m
   CLIPN_REQUIRE(d % 8 == 0 && d <= 1024 && d > 0, "layernorm: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return CLIPN_OK;
   int64_t blocks = (rows + 7) / 8;
-  const int cap = num_sms() * 2;  // one resident wave (2 blocks/SM): every block does a single dgamma/dbeta flush
+  const int cap = num_sms() * (d <= 512 ? 3 : 2);  // one resident wave: every block does a single dgamma/dbeta flush
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
 #define CLIPN_LN_BWD(N)                                                                                              \
   layernorm_bwd_kernel<N><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(BF(dy), BF(x), mean, rstd, gamma,          \
