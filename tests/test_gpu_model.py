@@ -149,3 +149,28 @@ def test_train_steps_reduce_loss():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < losses[0], losses
+
+
+def test_vitb16_siglip_config_forward_backward_vs_oracle():
+    """BASELINE config 5 shape family: ViT-B-16 (L = 197 -> general attention kernels) + SigLipLoss with logit_bias.
+    Features vs the fp32 oracle on the same (bf16-rounded) parameters; loss vs the oracle's SigLIP restatement."""
+    from open_clip_b200.loss import NativeSigLipLoss
+    cfg = O.CONFIGS["ViT-B-16"]
+    base = O.init_params(cfg, seed=3, bias_std=0.02, init_logit_scale=2.302585, init_logit_bias=-10.0)
+    image, text = O.synthetic_batch(cfg, 8, seed=5)
+    m = create_model("ViT-B-16", output_dict=True, init_logit_bias=-10.0)
+    m.load_reference_state_dict(base)
+    out = m(image=image.cuda().to(BF16), text=text.cuda())
+    loss = NativeSigLipLoss()(out["image_features"], out["text_features"], out["logit_scale"], out["logit_bias"])
+    loss.backward()
+    torch.cuda.synchronize()
+    p32 = {k: v.float() for k, v in O.cast_params(base, "bf16").items()}
+    with torch.no_grad():
+        ref = O.clip_forward(p32, cfg, image.to(BF16).float(), text)
+        ref_loss = O.siglip_block_loss(ref["image_features"], ref["text_features"], ref["logit_scale"], ref["logit_bias"])
+    for key in ("image_features", "text_features"):
+        got = out[key].float().cpu()
+        cos = torch.nn.functional.cosine_similarity(got, ref[key], dim=-1).min().item()
+        assert cos >= 0.9999 and (got - ref[key]).abs().max().item() <= 3e-3, (key, cos)
+    assert abs(float(loss) - float(ref_loss)) <= 2e-2 * abs(float(ref_loss)) + 1e-2
+    assert all(p.grad is not None and torch.isfinite(p.grad.float()).all() for p in m.parameters())
