@@ -124,7 +124,10 @@ int clipn_layernorm_bwd(const void* dy, const void* x, const float* mean, const 
  * causal != 0 reproduces the additive -inf upper-triangular mask (transformer.py:1716-1722). */
 int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
                         int32_t causal, float scale, clipn_stream_t stream);
-/* dbias (optional, fp32 [3*H*64], +=): column sums of dqkv == gradient of in_proj_bias, fused into the kernel */
+/* dbias (optional, fp32 [3*H*64], +=): column sums of dqkv == gradient of in_proj_bias, fused into the kernel.
+ * Sequence limits: L <= 640 (forward and backward). L <= 384 runs one kernel with Q,K,V,dO resident in shared
+ * memory and does not read `out`; 384 < L <= 640 (ViT-L/14-336: 577) runs a dQ pass with K,V resident and a
+ * dK/dV pass with Q,dO resident, both taking D = rowsum(dO o O) from `out`. */
 int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                         float* dbias, int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
                         clipn_stream_t stream);
@@ -134,6 +137,15 @@ int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, cons
  * [B,3,H,W] -> patches bf16 [B*gh*gw, 3*P*P], column order (c, py, px) == conv1.weight.flatten(1). */
 int clipn_patchify(const void* image, void* patches, int32_t batch, int32_t chans, int32_t height, int32_t width,
                    int32_t patch, clipn_stream_t stream);
+/* Same im2row for any even patch size (ViT-L/14: 3*14*14 = 588 columns, whose rows are not 16-byte multiples):
+ * rows are written with pitch ld_patches (multiple of 8, >= chans*patch*patch) and zero-filled beyond the data,
+ * so the conv1 GEMM runs with K = ld_patches. With height == width == patch it pads a [d,3,P,P] weight the same
+ * way (one "patch" per output channel). */
+int clipn_patchify_padded(const void* image, void* patches, int64_t ld_patches, int32_t batch, int32_t chans,
+                          int32_t height, int32_t width, int32_t patch, clipn_stream_t stream);
+/* dst[r, 0:cols] += src[r, 0:cols] (fp32): folds a K-padded conv1 weight gradient back into the parameter layout */
+int clipn_accum_rows_f32(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows, int32_t cols,
+                         clipn_stream_t stream);
 /* x[b,0,:] = bf16(bf16(cls)+bf16(pos[0])); x[b,1+p,:] = bf16(patch_out[b*np+p] + bf16(pos[1+p]))
  * (transformer.py:799-801) */
 int clipn_vision_embed_fwd(const void* patch_out, const float* cls, const float* pos, void* x, int32_t batch,

@@ -53,6 +53,8 @@ SIGNATURES = {
     "clipn_attention_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "clipn_attention_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "clipn_patchify": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+    "clipn_patchify_padded": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P]),
+    "clipn_accum_rows_f32": (C.c_int, [_P, _I64, _P, _I64, _I64, _I32, _P]),
     "clipn_vision_embed_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clipn_vision_embed_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P]),
     "clipn_text_embed_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),

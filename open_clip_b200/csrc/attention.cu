@@ -19,6 +19,7 @@ namespace clipn {
 
 constexpr int HD = 64;   // head dim
 constexpr int LDS = 72;  // padded smem row (bf16 elements): 144 B => conflict-free fragment loads
+constexpr int kLongSeqMax = 640;  // longest sequence the K,V-resident kernels hold in 227 KB
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
@@ -589,6 +590,334 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Long sequences (L > 384, e.g. ViT-L/14-336: 577 tokens): the whole Q/K/V/dO set no longer fits in shared memory.
+// Forward and the dQ pass keep K,V of the (batch, head) item resident and stream 16-row Q (and dO) tiles through a
+// per-warp staging tile; the dK/dV pass keeps Q,dO resident and streams K,V tiles.  D = rowsum(dO o O) is taken
+// from the forward output (one extra tile read) instead of a P.dP sweep.  One CTA (8 warps) per SM.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_tile_load(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t src_ld, int r0,
+                                               int seq, int lane) {
+  for (int i = lane; i < 16 * 8; i += 32) {
+    const int r = i >> 3, v = i & 7;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (r0 + r < seq) val = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(r0 + r) * src_ld + v * 8);
+    *reinterpret_cast<uint4*>(dst + r * LDS + v * 8) = val;
+  }
+}
+// D[r] = sum_c dO[r,c] * O[r,c] for the 16 rows of a staged dO tile (O read from global); result in sDw[0..15]
+__device__ __forceinline__ void warp_tile_rowdot(const __nv_bfloat16* sDOt, const __nv_bfloat16* o_base, int64_t o_ld,
+                                                 int r0, int seq, float* sDw, int lane) {
+  const int r = lane >> 1, hf = lane & 1;
+  float acc = 0.f;
+  if (r0 + r < seq) {
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      float a[8], c[8];
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(o_base + static_cast<int64_t>(r0 + r) * o_ld + hf * 32 + v * 8), a);
+      unpack_bf16x8(*reinterpret_cast<const uint4*>(sDOt + r * LDS + hf * 32 + v * 8), c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc += a[j] * c[j];
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (hf == 0) sDw[r] = acc;
+}
+
+__global__ void __launch_bounds__(256, 1)
+attention_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+                          float* __restrict__ lse_out, int items, int seq, int heads, int causal, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int Lp = (seq + 15) & ~15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sV = sK + Lp * LDS;
+  __nv_bfloat16* sQt = sV + Lp * LDS + warp * 16 * LDS;  // this warp's Q tile, later its output staging tile
+  const int d = heads * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(d);
+  const float sl2 = scale * kLog2e;
+  tile_zero_pad(sK, seq, Lp);
+  tile_zero_pad(sV, seq, Lp);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    tile_cp_async(sK, base + d, ld, seq);
+    tile_cp_async(sV, base + 2 * d, ld, seq);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      warp_tile_load(sQt, base, ld, r0, seq, lane);
+      __syncwarp();
+      uint32_t qa[4][4];
+      load_a_frags(sQt, 0, lane, qa);
+      float m_i[2] = {-INFINITY, -INFINITY}, l_i[2] = {0.f, 0.f};
+      float o[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[j][e] = 0.f;
+      const int row_a = r0 + (lane >> 2);
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      for (int kc = 0; kc < kv_end; kc += 64) {
+        float sc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+          if (kc + j * 8 < kv_end) mma_a_tT(sc[j], qa, sK, kc + j * 8, lane);
+        }
+        float cmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = kc + j * 8 + (lane & 3) * 2 + (e & 1);
+            const int row = row_a + (e >> 1) * 8;
+            const bool ok = key < kv_end && !(causal && key > row);
+            sc[j][e] = ok ? sc[j][e] * sl2 : -INFINITY;
+            cmax[e >> 1] = fmaxf(cmax[e >> 1], sc[j][e]);
+          }
+        float corr[2], mref[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 1));
+          cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 2));
+          const float mn = fmaxf(m_i[t], cmax[t]);
+          mref[t] = (mn == -INFINITY) ? 0.f : mn;
+          corr[t] = exp2f(m_i[t] - mref[t]);
+          m_i[t] = mn;
+          l_i[t] *= corr[t];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[j][e] *= corr[e >> 1];
+            sc[j][e] = exp2f(sc[j][e] - mref[e >> 1]);
+            l_i[e >> 1] += sc[j][e];
+          }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kc + kk * 16 < kv_end) {
+            uint32_t pa[4];
+            pack_frag(pa, sc[2 * kk], sc[2 * kk + 1]);
+            mma_p_t(o, pa, sV, kc + kk * 16, lane);
+          }
+        }
+      }
+      float inv[2];
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 1);
+        l_i[t] += __shfl_xor_sync(0xffffffffu, l_i[t], 2);
+        inv[t] = l_i[t] > 0.f ? 1.f / l_i[t] : 0.f;
+      }
+      __syncwarp();
+      stage_frag_tile(sQt, o, inv[0], inv[1], lane);
+      __syncwarp();
+      store_tile16(sQt, out + static_cast<int64_t>(b) * seq * d + h * HD, d, r0, seq, lane);
+      if ((lane & 3) == 0 && lse_out != nullptr) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int r = row_a + t * 8;
+          if (r < seq) lse_out[(static_cast<int64_t>(b) * heads + h) * seq + r] = (m_i[t] + log2f(l_i[t])) * kLn2;
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+// dQ pass: K,V resident; per warp: Q and dO tiles staged, D from dO o O, S/dP recomputed per 16-key slab.
+__global__ void __launch_bounds__(256, 1)
+attention_bwd_long_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                             const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse_in,
+                             __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int items, int seq, int heads,
+                             int causal, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int Lp = (seq + 15) & ~15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sV = sK + Lp * LDS;
+  __nv_bfloat16* sQt = sV + Lp * LDS + warp * 32 * LDS;
+  __nv_bfloat16* sDOt = sQt + 16 * LDS;
+  float* sDw = reinterpret_cast<float*>(sV + Lp * LDS + nwarps * 32 * LDS) + warp * 16;
+  const int d = heads * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(d);
+  const float sl2 = scale * kLog2e;
+  tile_zero_pad(sK, seq, Lp);
+  tile_zero_pad(sV, seq, Lp);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    const __nv_bfloat16* obase = out + static_cast<int64_t>(b) * seq * d + h * HD;
+    const __nv_bfloat16* dobase = dout + static_cast<int64_t>(b) * seq * d + h * HD;
+    const float* lse_b = lse_in + (static_cast<int64_t>(b) * heads + h) * seq;
+    __nv_bfloat16* dq_base = dqkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    tile_cp_async(sK, base + d, ld, seq);
+    tile_cp_async(sV, base + 2 * d, ld, seq);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int r0 = warp * 16; r0 < Lp; r0 += nwarps * 16) {
+      warp_tile_load(sQt, base, ld, r0, seq, lane);
+      warp_tile_load(sDOt, dobase, d, r0, seq, lane);
+      __syncwarp();
+      warp_tile_rowdot(sDOt, obase, d, r0, seq, sDw, lane);
+      __syncwarp();
+      uint32_t qa[4][4], doa[4][4];
+      load_a_frags(sQt, 0, lane, qa);
+      load_a_frags(sDOt, 0, lane, doa);
+      const int row_a = r0 + (lane >> 2);
+      const float lse_r[2] = {row_a < seq ? lse_b[row_a] * kLog2e : 0.f, row_a + 8 < seq ? lse_b[row_a + 8] * kLog2e : 0.f};
+      const float d_r[2] = {sDw[lane >> 2], sDw[(lane >> 2) + 8]};
+      float dq[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[j][e] = 0.f;
+      int kv_end = seq;
+      if (causal && r0 + 16 < kv_end) kv_end = r0 + 16;
+      for (int k0 = 0; k0 < kv_end; k0 += 16) {
+        float ds[2][4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          if (k0 + t * 8 < kv_end) {
+            mma_a_tT(sc, qa, sK, k0 + t * 8, lane);
+            mma_a_tT(dp, doa, sV, k0 + t * 8, lane);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int key = k0 + t * 8 + (lane & 3) * 2 + (e & 1);
+            const int row = row_a + (e >> 1) * 8;
+            const bool ok = key < kv_end && row < seq && !(causal && key > row);
+            ds[t][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
+          }
+        }
+        uint32_t pa[4];
+        pack_frag(pa, ds[0], ds[1]);
+        mma_p_t(dq, pa, sK, k0, lane);
+      }
+      __syncwarp();
+      stage_frag_tile(sQt, dq, scale, scale, lane);
+      __syncwarp();
+      store_tile16(sQt, dq_base, ld, r0, seq, lane);
+      if (dbias != nullptr) tile_colsum_atomic(sQt, dbias + h * HD, lane);
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
+// dK/dV pass: Q,dO (and D, LSE) resident; per warp: K and V tiles staged; transposed tiles as in the general kernel.
+__global__ void __launch_bounds__(256, 1)
+attention_bwd_long_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ out,
+                              const __nv_bfloat16* __restrict__ dout, const float* __restrict__ lse_in,
+                              __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dbias, int items, int seq, int heads,
+                              int causal, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_att[];
+  const int Lp = (seq + 15) & ~15;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_att);
+  __nv_bfloat16* sDO = sQ + Lp * LDS;
+  __nv_bfloat16* sKt = sDO + Lp * LDS + warp * 32 * LDS;
+  __nv_bfloat16* sVt = sKt + 16 * LDS;
+  float* sLse = reinterpret_cast<float*>(sDO + Lp * LDS + nwarps * 32 * LDS);
+  float* sD = sLse + Lp;
+  const int d = heads * HD;
+  const int64_t ld = 3 * static_cast<int64_t>(d);
+  const float sl2 = scale * kLog2e;
+  tile_zero_pad(sQ, seq, Lp);
+  tile_zero_pad(sDO, seq, Lp);
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int b = item / heads, h = item % heads;
+    const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    const __nv_bfloat16* obase = out + static_cast<int64_t>(b) * seq * d + h * HD;
+    const __nv_bfloat16* dobase = dout + static_cast<int64_t>(b) * seq * d + h * HD;
+    __nv_bfloat16* dq_base = dqkv + static_cast<int64_t>(b) * seq * ld + h * HD;
+    tile_cp_async(sQ, base, ld, seq);
+    tile_cp_async(sDO, dobase, d, seq);
+    cp_async_commit();
+    for (int i = threadIdx.x; i < Lp; i += blockDim.x)
+      sLse[i] = (i < seq) ? lse_in[(static_cast<int64_t>(b) * heads + h) * seq + i] * kLog2e : 0.f;
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int i = threadIdx.x; i < Lp * 8; i += blockDim.x) {  // D[r] = sum_c dO[r,c] O[r,c]  (8 lanes per row)
+      const int r = i >> 3, v = i & 7;
+      float acc = 0.f;
+      if (r < seq) {
+        float a[8], c[8];
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(obase + static_cast<int64_t>(r) * d + v * 8), a);
+        unpack_bf16x8(*reinterpret_cast<const uint4*>(sDO + r * LDS + v * 8), c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += a[j] * c[j];
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if (v == 0) sD[r] = acc;
+    }
+    __syncthreads();
+    for (int c0 = warp * 16; c0 < Lp; c0 += nwarps * 16) {
+      warp_tile_load(sKt, base + d, ld, c0, seq, lane);
+      warp_tile_load(sVt, base + 2 * d, ld, c0, seq, lane);
+      __syncwarp();
+      uint32_t ka[4][4], va[4][4];
+      load_a_frags(sKt, 0, lane, ka);
+      load_a_frags(sVt, 0, lane, va);
+      const int key_a = c0 + (lane >> 2);
+      float dk[8][4], dv[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dk[j][e] = dv[j][e] = 0.f;
+      const int q_begin = causal ? c0 : 0;
+      for (int q0 = q_begin; q0 < seq; q0 += 16) {
+        float pt[2][4], dst[2][4];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          float sc[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+          const bool live = q0 + t * 8 < seq;
+          if (live) {
+            mma_a_tT(sc, ka, sQ, q0 + t * 8, lane);
+            mma_a_tT(dp, va, sDO, q0 + t * 8, lane);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int qi = q0 + t * 8 + (lane & 3) * 2 + (e & 1);
+            const int key = key_a + (e >> 1) * 8;
+            const bool ok = live && qi < seq && key < seq && !(causal && key > qi);
+            const float p = ok ? exp2f(sc[e] * sl2 - sLse[qi]) : 0.f;
+            pt[t][e] = p;
+            dst[t][e] = ok ? p * (dp[e] - sD[qi]) : 0.f;
+          }
+        }
+        uint32_t pa[4], da[4];
+        pack_frag(pa, pt[0], pt[1]);
+        pack_frag(da, dst[0], dst[1]);
+        mma_p_t(dv, pa, sDO, q0, lane);
+        mma_p_t(dk, da, sQ, q0, lane);
+      }
+      __syncwarp();
+      stage_frag_tile(sKt, dk, scale, scale, lane);
+      stage_frag_tile(sVt, dv, 1.f, 1.f, lane);
+      __syncwarp();
+      store_tile16(sKt, dq_base + d, ld, c0, seq, lane);
+      store_tile16(sVt, dq_base + 2 * d, ld, c0, seq, lane);
+      if (dbias != nullptr) {
+        tile_colsum_atomic(sKt, dbias + d + h * HD, lane);
+        tile_colsum_atomic(sVt, dbias + 2 * d + h * HD, lane);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
+}
+
 static int pick_warps(int seq) {
   int tiles = (seq + 15) / 16;
   return tiles < 8 ? tiles : 8;
@@ -607,8 +936,18 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
   const size_t stage_bytes = static_cast<size_t>(3) * Lp * LDS * 2;
   const int nst = (2 * stage_bytes <= 113 * 1024) ? 2 : 1;  // double-buffer when two CTAs still fit per SM
   const size_t smem = nst * stage_bytes;
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_fwd: sequence too long for the in-smem kernel (L <= 512)");
   const int items = batch * heads;
+  if (smem > 227 * 1024) {  // K,V resident, Q streamed per warp
+    const size_t smem_long = (static_cast<size_t>(2) * Lp + 8 * 16) * LDS * 2;
+    CLIPN_REQUIRE(smem_long <= 227 * 1024 && seq <= kLongSeqMax, "attention_fwd: sequence too long (L <= 640)");
+    int grid_long = num_sms() < items ? num_sms() : items;
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_fwd_long_kernel<<<grid_long, 256, smem_long, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), lse, items, seq, heads, causal,
+        scale);
+    CLIPN_CHECK_CUDA(cudaGetLastError());
+    return CLIPN_OK;
+  }
   const int nw = pick_warps(seq);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   const int cap = nw <= 5 ? 3 : 2;
@@ -635,7 +974,7 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
 extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                                    float* dbias, int32_t batch, int32_t seq, int32_t heads, int32_t causal, float scale,
                                    clipn_stream_t stream) {
-  (void)out;  // D = rowsum(dO o O) is recomputed as sum_j P_ij dP_ij: the forward output is not re-read
+  // L <= 384: D = rowsum(dO o O) is recomputed as sum_j P_ij dP_ij and `out` is not read; longer sequences read it
   CLIPN_REQUIRE(qkv && dout && lse && dqkv, "attention_bwd: null pointer");
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_bwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
@@ -675,8 +1014,31 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   const size_t extra = static_cast<size_t>(nw) * 16 * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);
   const int nst = (2 * stage_bytes + extra <= 113 * 1024) ? 2 : 1;
   const size_t smem = nst * stage_bytes + extra;
-  CLIPN_REQUIRE(smem <= 227 * 1024, "attention_bwd: sequence too long for the in-smem kernel (L <= 384)");
   const int items = batch * heads;
+  if (smem > 227 * 1024) {  // two passes: dQ with K,V resident, then dK/dV with Q,dO resident; D from dO o O
+    CLIPN_REQUIRE(out != nullptr, "attention_bwd: the long-sequence path needs the forward output");
+    const size_t smem_dq = (static_cast<size_t>(2) * Lp + 8 * 32) * LDS * 2 + 8 * 16 * sizeof(float);
+    const size_t smem_dkv = (static_cast<size_t>(2) * Lp + 8 * 32) * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);
+    CLIPN_REQUIRE(smem_dq <= 227 * 1024 && smem_dkv <= 227 * 1024 && seq <= kLongSeqMax,
+                  "attention_bwd: sequence too long (L <= 640)");
+    const int grid_long = num_sms() < items ? num_sms() : items;
+    auto stl = static_cast<cudaStream_t>(stream);
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_long_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_long_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attention_bwd_long_dq_kernel<<<grid_long, 256, smem_dq, stl>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
+        reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), nullptr, items, seq,
+        heads, causal, scale);
+    attention_bwd_long_dkv_kernel<<<grid_long, 256, smem_dkv, stl>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(out),
+        reinterpret_cast<const __nv_bfloat16*>(dout), lse, reinterpret_cast<__nv_bfloat16*>(dqkv), nullptr, items, seq,
+        heads, causal, scale);
+    CLIPN_CHECK_CUDA(cudaGetLastError());
+    if (dbias != nullptr)
+      return clipn_colsum(dqkv, 3 * static_cast<int64_t>(heads) * HD, dbias, static_cast<int64_t>(batch) * seq,
+                          3 * heads * HD, stream);
+    return CLIPN_OK;
+  }
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;

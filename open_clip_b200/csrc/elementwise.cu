@@ -192,6 +192,46 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
 // ------------------------------------------------------------------------------------------------
 // patchify (im2row for conv1 with kernel == stride): patches[b*np + gy*gw + gx][c*P*P + py*P + px]
 // ------------------------------------------------------------------------------------------------
+// Any even patch size (ViT-L/14: 14 px = 28 B per patch row, not 16-byte aligned): one bf16 pair per thread in
+// OUTPUT order, so writes are coalesced; columns [chans*patch*patch, ld) are zero-filled (K padding for TMA).
+__global__ void __launch_bounds__(256) patchify_pair_kernel(const __nv_bfloat16* __restrict__ img,
+                                                            __nv_bfloat16* __restrict__ out, int64_t ld, int batch,
+                                                            int chans, int height, int width, int patch) {
+  const int gw = width / patch, gh = height / patch;
+  const int kcols = chans * patch * patch;
+  const int pairs = static_cast<int>(ld / 2);
+  const int64_t total = static_cast<int64_t>(batch) * gh * gw * pairs;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % pairs) * 2;
+    const int64_t prow = i / pairs;
+    uint32_t v = 0u;
+    if (col < kcols) {
+      const int px = col % patch;
+      const int py = (col / patch) % patch;
+      const int c = col / (patch * patch);
+      const int gx = static_cast<int>(prow % gw);
+      const int gy = static_cast<int>((prow / gw) % gh);
+      const int64_t b = prow / (static_cast<int64_t>(gw) * gh);
+      v = *reinterpret_cast<const uint32_t*>(img + ((b * chans + c) * height + gy * patch + py) * width + gx * patch + px);
+    }
+    *reinterpret_cast<uint32_t*>(out + prow * ld + col) = v;
+  }
+}
+
+// dst[r][c] += src[r][c] for c < cols (fp32; un-pads a K-padded weight gradient into the parameter's own layout)
+__global__ void __launch_bounds__(256) accum_rows_f32_kernel(float* __restrict__ dst, int64_t ld_dst,
+                                                             const float* __restrict__ src, int64_t ld_src, int64_t rows,
+                                                             int cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i % cols);
+    dst[r * ld_dst + c] += src[r * ld_src + c];
+  }
+}
+
 __global__ void __launch_bounds__(256) patchify_kernel(const __nv_bfloat16* __restrict__ img,
                                                        __nv_bfloat16* __restrict__ out, int batch, int chans, int height,
                                                        int width, int patch) {
@@ -544,6 +584,31 @@ extern "C" int clipn_patchify(const void* image, void* patches, int32_t batch, i
   const int64_t total = static_cast<int64_t>(batch) * chans * height * (width / 8);
   if (total <= 0) return CLIPN_OK;
   patchify_kernel<<<grid_for_elems(total), 256, 0, ST(stream)>>>(BF(image), BFW(patches), batch, chans, height, width, patch);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+extern "C" int clipn_patchify_padded(const void* image, void* patches, int64_t ld_patches, int32_t batch, int32_t chans,
+                                     int32_t height, int32_t width, int32_t patch, clipn_stream_t stream) {
+  CLIPN_REQUIRE(image && patches, "patchify_padded: null pointer");
+  CLIPN_REQUIRE(patch > 0 && patch % 2 == 0 && width % 2 == 0, "patchify_padded: patch and width must be even");
+  CLIPN_REQUIRE(height % patch == 0 && width % patch == 0, "patchify_padded: image must be a whole number of patches");
+  CLIPN_REQUIRE(ld_patches % 8 == 0 && ld_patches >= static_cast<int64_t>(chans) * patch * patch,
+                "patchify_padded: row pitch must be a multiple of 8 and hold chans*patch*patch columns");
+  const int64_t total = static_cast<int64_t>(batch) * (height / patch) * (width / patch) * (ld_patches / 2);
+  if (total <= 0) return CLIPN_OK;
+  patchify_pair_kernel<<<grid_for_elems(total), 256, 0, ST(stream)>>>(BF(image), BFW(patches), ld_patches, batch, chans,
+                                                                      height, width, patch);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+extern "C" int clipn_accum_rows_f32(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows,
+                                    int32_t cols, clipn_stream_t stream) {
+  CLIPN_REQUIRE(dst && src, "accum_rows_f32: null pointer");
+  CLIPN_REQUIRE(cols > 0 && ld_dst >= cols && ld_src >= cols, "accum_rows_f32: bad pitch");
+  if (rows <= 0) return CLIPN_OK;
+  accum_rows_f32_kernel<<<grid_for_elems(rows * cols), 256, 0, ST(stream)>>>(dst, ld_dst, src, ld_src, rows, cols);
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }

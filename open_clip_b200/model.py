@@ -74,7 +74,8 @@ class _TowerFn(torch.autograd.Function):
         P = dict(zip(names, params))
         cfg = model._vcfg if which == "visual" else model._tcfg
         fwd = tower.vision_forward if which == "visual" else tower.text_forward
-        feat, saved = fwd(P, cfg, inp, normalize, model._scratch[which], need_grad)
+        feat, saved = fwd(P, cfg, inp, normalize, model._scratch[which], need_grad,
+                          checkpoint=bool(model.grad_checkpointing))
         ctx.model, ctx.which, ctx.saved, ctx.P, ctx.names = model, which, saved, P, names
         return feat
 
@@ -232,7 +233,8 @@ class NativeCLIP(nn.Module):
 
     # ------------------------------------------------------------------ reference API surface
     def set_grad_checkpointing(self, enable: bool = True, impl: str = "inline"):
-        # model.py:377-379. Activation storage here is already 10*d/token with LN/GELU recompute.
+        # model.py:377-379 / transformer.py:397-402: keep only each block's input and re-run the block in the
+        # backward (d bf16 per token per block instead of 10-16*d; one extra block forward per block).
         self.grad_checkpointing = enable
 
     def lock_image_tower(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
@@ -295,6 +297,9 @@ CONFIGS = {
                      text_cfg=dict(context_length=77, vocab_size=49408, width=512, heads=8, layers=12)),
     "ViT-B-16": dict(embed_dim=512, vision_cfg=dict(image_size=224, layers=12, width=768, patch_size=16),
                      text_cfg=dict(context_length=77, vocab_size=49408, width=512, heads=8, layers=12)),
+    # model_configs/ViT-L-14-336.json (577 tokens: long-sequence attention kernels; patch 14: K-padded im2row)
+    "ViT-L-14-336": dict(embed_dim=768, vision_cfg=dict(image_size=336, layers=24, width=1024, patch_size=14),
+                         text_cfg=dict(context_length=77, vocab_size=49408, width=768, heads=12, layers=12)),
     "tiny": dict(embed_dim=128, vision_cfg=dict(image_size=64, layers=2, width=128, patch_size=16),
                  text_cfg=dict(context_length=20, vocab_size=512, width=128, heads=2, layers=2)),
 }

@@ -152,12 +152,32 @@ def attention_bwd(qkv, o, do, lse, batch, seq, heads, causal, out=None, dbias=No
     return dqkv
 
 
+def patch_cols(chans, patch):
+    """Row length of the im2row matrix: chans*patch*patch rounded up to 8 (TMA wants 16-byte row pitches)."""
+    return (chans * patch * patch + 7) // 8 * 8
+
+
 def patchify(image, patch):
+    """im2row for conv1. Returns [B*gh*gw, patch_cols]; columns beyond chans*patch*patch (patch 14 only) are zero."""
     _chk(image, BF16, "patchify.image")
     B, Cc, H, W = image.shape
-    out = torch.empty((B * (H // patch) * (W // patch), Cc * patch * patch), dtype=BF16, device=image.device)
-    _call(L.lib().clipn_patchify(image.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, _stream()))
+    k = Cc * patch * patch
+    if patch % 8 == 0:
+        out = torch.empty((B * (H // patch) * (W // patch), k), dtype=BF16, device=image.device)
+        _call(L.lib().clipn_patchify(image.data_ptr(), out.data_ptr(), B, Cc, H, W, patch, _stream()))
+        return out
+    ld = patch_cols(Cc, patch)
+    out = torch.empty((B * (H // patch) * (W // patch), ld), dtype=BF16, device=image.device)
+    _call(L.lib().clipn_patchify_padded(image.data_ptr(), out.data_ptr(), ld, B, Cc, H, W, patch, _stream()))
     return out
+
+
+def accum_rows_f32(dst, src, cols):
+    """dst[:, :cols] += src[:, :cols] (fp32, row pitches from the tensors)."""
+    _chk(dst, F32, "accum.dst"); _chk(src, F32, "accum.src")
+    _call(L.lib().clipn_accum_rows_f32(dst.data_ptr(), dst.stride(0), src.data_ptr(), src.stride(0), dst.shape[0], cols,
+                                       _stream()))
+    return dst
 
 
 def vision_embed_fwd(patch_out, cls, pos, batch, npatch):

@@ -84,8 +84,36 @@ class BlockSaved:
 @dataclass
 class TowerSaved:
     batch: int = 0
-    blocks: List[BlockSaved] = field(default_factory=list)
+    # per block: BlockSaved, or (grad checkpointing, transformer.py:397-402) just the block's input tensor
+    blocks: List[object] = field(default_factory=list)
     extra: Dict[str, torch.Tensor] = field(default_factory=dict)
+
+
+def _run_blocks(P, cfg: TowerCfg, x: torch.Tensor, B: int, ws: Scratch, saved: Optional[TowerSaved], checkpoint: bool):
+    """The residual stack. With `checkpoint` only each block's input (d bf16 per token) is kept and the block is
+    re-run in the backward — the reference's `checkpoint(r, x)` loop (transformer.py:397-402)."""
+    for i in range(cfg.layers):
+        pre = f"{cfg.prefix}.resblocks.{i}"
+        if saved is not None and checkpoint:
+            saved.blocks.append(x)
+            x, _ = block_forward(P, pre, cfg, x, B, ws, False)
+        else:
+            x, bs = block_forward(P, pre, cfg, x, B, ws, saved is not None)
+            if saved is not None:
+                saved.blocks.append(bs)
+    return x
+
+
+def _run_blocks_backward(P, G, cfg: TowerCfg, saved: TowerSaved, dx: torch.Tensor, B: int, ws: Scratch):
+    for i in reversed(range(cfg.layers)):
+        pre = f"{cfg.prefix}.resblocks.{i}"
+        s = saved.blocks[i]
+        if isinstance(s, torch.Tensor):  # checkpointed: recompute this block's activations from its input
+            _, s = block_forward(P, pre, cfg, s, B, ws, True)
+        dx = block_backward(P, G, pre, cfg, s, dx, B, ws)
+        saved.blocks[i] = None  # free activations as we go
+        del s
+    return dx
 
 
 # --------------------------------------------------------------------------------------------------
@@ -216,7 +244,16 @@ def _head_backward(dfeat, saved: TowerSaved, ln_w, proj, g_ln_w, g_ln_b, g_proj,
 # --------------------------------------------------------------------------------------------------
 # vision tower
 # --------------------------------------------------------------------------------------------------
-def vision_forward(P, cfg: TowerCfg, image: torch.Tensor, normalize: bool, ws: Scratch, save: bool):
+def _conv1_weight_rows(w4: torch.Tensor, patch: int) -> torch.Tensor:
+    """conv1.weight [d,3,P,P] as the GEMM's [d, K] operand; for patch 14 a zero-padded copy with K = 592 (the same
+    im2row kernel with one 'patch' per output channel does the padding)."""
+    if patch % 8 == 0:
+        return w4.view(w4.shape[0], -1)
+    return ops.patchify(w4, patch)
+
+
+def vision_forward(P, cfg: TowerCfg, image: torch.Tensor, normalize: bool, ws: Scratch, save: bool,
+                   checkpoint: bool = False):
     B = image.shape[0]
     if image.dtype != BF16:
         image = image.to(BF16)  # prepare_batch casts inputs to the model's input dtype (base_task.py:148-152)
@@ -226,16 +263,13 @@ def vision_forward(P, cfg: TowerCfg, image: torch.Tensor, normalize: bool, ws: S
     d = cfg.width
     saved = TowerSaved(batch=B) if save else None
     patches = ops.patchify(image, cfg.patch)
-    w = P["visual.conv1.weight"].view(d, -1)
+    w = _conv1_weight_rows(P["visual.conv1.weight"], cfg.patch)
     pe = ops.gemm(patches, w)
     x0 = ops.vision_embed_fwd(pe, P["visual.class_embedding"], P["visual.positional_embedding"], B, npatch)
     x, m0, r0 = ops.layernorm_fwd(x0, P["visual.ln_pre.weight"], P["visual.ln_pre.bias"], save_stats=save)
     if save:
         saved.extra.update(patches=patches, x0=x0, pre_mean=m0, pre_rstd=r0)
-    for i in range(cfg.layers):
-        x, bs = block_forward(P, f"{cfg.prefix}.resblocks.{i}", cfg, x, B, ws, save)
-        if save:
-            saved.blocks.append(bs)
+    x = _run_blocks(P, cfg, x, B, ws, saved, checkpoint)
     feat = _head_forward(x, None, P["visual.ln_post.weight"], P["visual.ln_post.bias"], P["visual.proj"], B, cfg.seq,
                          normalize, saved)
     return feat, saved
@@ -248,30 +282,34 @@ def vision_backward(P, G, cfg: TowerCfg, saved: TowerSaved, dfeat: torch.Tensor,
     npatch = grid * grid
     dx = _head_backward(dfeat, saved, P["visual.ln_post.weight"], P["visual.proj"], G["visual.ln_post.weight"],
                         G["visual.ln_post.bias"], G["visual.proj"], B, cfg.seq, ws, d)
-    for i in reversed(range(cfg.layers)):
-        dx = block_backward(P, G, f"{cfg.prefix}.resblocks.{i}", cfg, saved.blocks[i], dx, B, ws)
-        saved.blocks[i] = None  # free activations as we go
+    dx = _run_blocks_backward(P, G, cfg, saved, dx, B, ws)
     e = saved.extra
     dx0 = ops.layernorm_bwd(dx, e["x0"], e["pre_mean"], e["pre_rstd"], P["visual.ln_pre.weight"],
                             G["visual.ln_pre.weight"], G["visual.ln_pre.bias"])
     dpe = ops.vision_embed_bwd(dx0, G["visual.class_embedding"], G["visual.positional_embedding"], B, npatch)
-    _wgrad(dpe, e["patches"], G["visual.conv1.weight"].view(d, -1))
+    gw = G["visual.conv1.weight"].view(d, -1)
+    k, kp = gw.shape[1], e["patches"].shape[1]
+    if kp == k:
+        _wgrad(dpe, e["patches"], gw)
+    else:  # patch 14: the im2row matrix is K-padded; accumulate into a padded scratch and fold the valid columns back
+        gw_pad = ws.get("conv1_grad_pad", (d, kp), F32, dpe.device)
+        gw_pad.zero_()
+        _wgrad(dpe, e["patches"], gw_pad)
+        ops.accum_rows_f32(gw, gw_pad, k)
 
 
 # --------------------------------------------------------------------------------------------------
 # text tower
 # --------------------------------------------------------------------------------------------------
-def text_forward(P, cfg: TowerCfg, text: torch.Tensor, normalize: bool, ws: Scratch, save: bool):
+def text_forward(P, cfg: TowerCfg, text: torch.Tensor, normalize: bool, ws: Scratch, save: bool,
+                 checkpoint: bool = False):
     B = text.shape[0]
     text = text.contiguous()
     saved = TowerSaved(batch=B) if save else None
     x, eot = ops.text_embed_fwd(text, P["token_embedding.weight"], P["positional_embedding"])
     if save:
         saved.extra.update(text=text)
-    for i in range(cfg.layers):
-        x, bs = block_forward(P, f"{cfg.prefix}.resblocks.{i}", cfg, x, B, ws, save)
-        if save:
-            saved.blocks.append(bs)
+    x = _run_blocks(P, cfg, x, B, ws, saved, checkpoint)
     feat = _head_forward(x, eot, P["ln_final.weight"], P["ln_final.bias"], P["text_projection"], B, cfg.seq, normalize,
                          saved)
     return feat, saved
@@ -282,7 +320,5 @@ def text_backward(P, G, cfg: TowerCfg, saved: TowerSaved, dfeat: torch.Tensor, w
     d = cfg.width
     dx = _head_backward(dfeat, saved, P["ln_final.weight"], P["text_projection"], G["ln_final.weight"],
                         G["ln_final.bias"], G["text_projection"], B, cfg.seq, ws, d)
-    for i in reversed(range(cfg.layers)):
-        dx = block_backward(P, G, f"{cfg.prefix}.resblocks.{i}", cfg, saved.blocks[i], dx, B, ws)
-        saved.blocks[i] = None
+    dx = _run_blocks_backward(P, G, cfg, saved, dx, B, ws)
     ops.text_embed_bwd(saved.extra["text"], dx, G["token_embedding.weight"], G["positional_embedding"])

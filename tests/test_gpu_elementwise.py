@@ -43,6 +43,28 @@ def test_patchify_matches_conv_unfold():
     assert rel_err(pe, conv) < 4e-3
 
 
+def test_patchify_patch14_padded_and_weight_grad_unpad():
+    """ViT-L/14: 588 columns padded to 592 (zero-filled) for both the im2row matrix and the conv1 weight; the K-padded
+    weight gradient is folded back into the [d, 588] parameter layout."""
+    B, P, H, d = 2, 14, 56, 128
+    img = randn(B, 3, H, H, seed=3)
+    patches = ops.patchify(img, P)
+    assert patches.shape == (B * 16, 592)
+    want = F.unfold(img.float(), kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
+    assert torch.equal(patches[:, :588].float(), want) and float(patches[:, 588:].float().abs().max()) == 0.0
+    w = randn(d, 3, P, P, seed=4, scale=0.05)
+    wp = ops.patchify(w, P)
+    assert torch.equal(wp[:, :588], w.view(d, -1)) and float(wp[:, 588:].float().abs().max()) == 0.0
+    pe = ops.gemm(patches, wp)
+    conv = F.conv2d(img.float(), w.float(), stride=P).reshape(B, d, -1).permute(0, 2, 1).reshape(-1, d)
+    assert rel_err(pe, conv) < 4e-3
+    gpad = torch.randn(d, 592, device="cuda")
+    g = torch.randn(d, 588, device="cuda")
+    want_g = g + gpad[:, :588]
+    ops.accum_rows_f32(g, gpad, 588)
+    assert torch.equal(g, want_g)
+
+
 def test_vision_embed_fwd_bwd():
     B, npatch, d = 5, 16, 128
     pe = randn(B * npatch, d, seed=1)

@@ -151,6 +151,44 @@ def test_train_steps_reduce_loss():
     assert losses[-1] < losses[0], losses
 
 
+def test_vitl14_336_geometry_and_grad_checkpointing_vs_oracle():
+    """BASELINE config 4 geometry (ViT-L/14-336: patch 14 -> K-padded im2row, 577 tokens -> long-sequence attention
+    kernels, width 1024 / 16 heads, text width 768) at reduced depth (2+2 blocks) so the fp32 oracle's autograd runs
+    in seconds. All gradients vs the oracle, then the same step with set_grad_checkpointing() (transformer.py:397-402)
+    must reproduce them."""
+    cfg = O.ClipCfg(embed_dim=768, image_size=336, patch_size=14, v_width=1024, v_layers=2, t_width=768, t_heads=12,
+                    t_layers=2)
+    base = O.init_params(cfg, seed=11, bias_std=0.02)
+    image, text = O.synthetic_batch(cfg, 4, seed=12)
+    m = NativeCLIP(768, vision_cfg=dict(image_size=336, layers=2, width=1024, patch_size=14),
+                   text_cfg=dict(context_length=77, vocab_size=49408, width=768, heads=12, layers=2), output_dict=True)
+    m.load_reference_state_dict(base)
+    out, loss = _run_native(m, image, text)
+    p32 = {k: v.detach().float().requires_grad_(True) for k, v in O.cast_params(base, "bf16").items()}
+    o = O.clip_forward(p32, cfg, image.to(BF16).float(), text)
+    ref_loss = O.clip_loss(o["image_features"], o["text_features"], o["logit_scale"])
+    ref_loss.backward()
+    _check_features(out, {k: o[k].detach() for k in ("image_features", "text_features")})
+    assert abs(float(loss) - float(ref_loss)) <= 1e-2
+    grads = {}
+    bad = []
+    for name, prm in m.named_parameters():
+        assert prm.grad is not None, name
+        grads[name] = prm.grad.detach().float().clone()
+        e = rel_err(prm.grad.cpu(), p32[name].grad)
+        if e > 3e-2:
+            bad.append((name, e))
+    assert not bad, bad
+    # checkpointed step: only block inputs are kept, blocks are re-run in the backward
+    m.set_grad_checkpointing(True)
+    for prm in m.parameters():
+        prm.grad = None
+    out2, loss2 = _run_native(m, image, text)
+    assert float(loss2) == float(loss)
+    worst = max((rel_err(prm.grad, grads[name]), name) for name, prm in m.named_parameters())
+    assert worst[0] < 2e-3, worst  # split-K accumulation order is the only difference
+
+
 def test_vitb16_siglip_config_forward_backward_vs_oracle():
     """BASELINE config 5 shape family: ViT-B-16 (L = 197 -> general attention kernels) + SigLipLoss with logit_bias.
     Features vs the fp32 oracle on the same (bf16-rounded) parameters; loss vs the oracle's SigLIP restatement."""
