@@ -198,15 +198,27 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
         }
         float cmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j) {
+          // only key tiles that cross the sequence end or the causal diagonal need the per-element predicate
+          const int k_lo = kc + j * 8;
+          const bool edge = (k_lo + 8 > kv_end) || (causal && k_lo + 7 > r0);  // warp-uniform
+          if (!edge) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int key = kc + j * 8 + (lane & 3) * 2 + (e & 1);
-            const int row = row_a + (e >> 1) * 8;
-            const bool ok = key < kv_end && !(causal && key > row);
-            sc[j][e] = ok ? sc[j][e] * sl2 : -INFINITY;
-            cmax[e >> 1] = fmaxf(cmax[e >> 1], sc[j][e]);
+            for (int e = 0; e < 4; ++e) {
+              sc[j][e] *= sl2;
+              cmax[e >> 1] = fmaxf(cmax[e >> 1], sc[j][e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int key = k_lo + (lane & 3) * 2 + (e & 1);
+              const int row = row_a + (e >> 1) * 8;
+              const bool ok = key < kv_end && !(causal && key > row);
+              sc[j][e] = ok ? sc[j][e] * sl2 : -INFINITY;
+              cmax[e >> 1] = fmaxf(cmax[e >> 1], sc[j][e]);
+            }
           }
+        }
         float corr[2], mref[2];
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -214,7 +226,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
           cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 2));
           const float mn = fmaxf(m_i[t], cmax[t]);
           mref[t] = (mn == -INFINITY) ? 0.f : mn;
-          corr[t] = exp2f(m_i[t] - mref[t]);  // m_i = -inf -> 0
+          corr[t] = ex2_approx(m_i[t] - mref[t]);  // m_i = -inf -> 0
           m_i[t] = mn;
           l_i[t] *= corr[t];
         }
@@ -223,7 +235,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             o[j][e] *= corr[e >> 1];
-            sc[j][e] = exp2f(sc[j][e] - mref[e >> 1]);
+            sc[j][e] = ex2_approx(sc[j][e] - mref[e >> 1]);
             l_i[e >> 1] += sc[j][e];
           }
 #pragma unroll
@@ -336,7 +348,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
           const int key = k0 + (lane & 3) * 2 + (e & 1);
           const int row = row_a + (e >> 1) * 8;
           const bool ok = key < kv_end && row < seq && !(causal && key > row);
-          if (ok) dsum[e >> 1] += exp2f(sc[e] * sl2 - lse_r[e >> 1]) * dp[e];
+          if (ok) dsum[e >> 1] += ex2_approx(sc[e] * sl2 - lse_r[e >> 1]) * dp[e];
         }
       }
 #pragma unroll
@@ -380,7 +392,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
             const int key = k0 + t * 8 + (lane & 3) * 2 + (e & 1);
             const int row = row_a + (e >> 1) * 8;
             const bool ok = key < kv_end && row < seq && !(causal && key > row);
-            ds[t][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
+            ds[t][e] = ok ? ex2_approx(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
           }
         }
         uint32_t pa[4];
@@ -420,7 +432,7 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
             const int qi = q0 + t * 8 + (lane & 3) * 2 + (e & 1);
             const int key = key_a + (e >> 1) * 8;
             const bool ok = live && qi < seq && key < seq && !(causal && key > qi);
-            const float p = ok ? exp2f(sc[e] * sl2 - sLse[qi]) : 0.f;
+            const float p = ok ? ex2_approx(sc[e] * sl2 - sLse[qi]) : 0.f;
             pt[t][e] = p;
             dst[t][e] = ok ? p * (dp[e] - sD[qi]) : 0.f;
           }
@@ -515,7 +527,7 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
           const int key = j * 8 + (lane & 3) * 2 + (e & 1);
           const int row = row_a + (e >> 1) * 8;
           const bool ok = key < kv_end && row < seq && !(causal && key > row);
-          p[j][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) : 0.f;
+          p[j][e] = ok ? ex2_approx(sc[e] * sl2 - lse_r[e >> 1]) : 0.f;
           dsum[e >> 1] += p[j][e] * dp[j][e];
         }
       }
@@ -686,7 +698,7 @@ attention_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
           cmax[t] = fmaxf(cmax[t], __shfl_xor_sync(0xffffffffu, cmax[t], 2));
           const float mn = fmaxf(m_i[t], cmax[t]);
           mref[t] = (mn == -INFINITY) ? 0.f : mn;
-          corr[t] = exp2f(m_i[t] - mref[t]);
+          corr[t] = ex2_approx(m_i[t] - mref[t]);
           m_i[t] = mn;
           l_i[t] *= corr[t];
         }
@@ -695,7 +707,7 @@ attention_fwd_long_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* 
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             o[j][e] *= corr[e >> 1];
-            sc[j][e] = exp2f(sc[j][e] - mref[e >> 1]);
+            sc[j][e] = ex2_approx(sc[j][e] - mref[e >> 1]);
             l_i[e >> 1] += sc[j][e];
           }
 #pragma unroll
@@ -795,7 +807,7 @@ attention_bwd_long_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_b
             const int key = k0 + t * 8 + (lane & 3) * 2 + (e & 1);
             const int row = row_a + (e >> 1) * 8;
             const bool ok = key < kv_end && row < seq && !(causal && key > row);
-            ds[t][e] = ok ? exp2f(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
+            ds[t][e] = ok ? ex2_approx(sc[e] * sl2 - lse_r[e >> 1]) * (dp[e] - d_r[e >> 1]) : 0.f;
           }
         }
         uint32_t pa[4];
@@ -891,7 +903,7 @@ attention_bwd_long_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_
             const int qi = q0 + t * 8 + (lane & 3) * 2 + (e & 1);
             const int key = key_a + (e >> 1) * 8;
             const bool ok = live && qi < seq && key < seq && !(causal && key > qi);
-            const float p = ok ? exp2f(sc[e] * sl2 - sLse[qi]) : 0.f;
+            const float p = ok ? ex2_approx(sc[e] * sl2 - sLse[qi]) : 0.f;
             pt[t][e] = p;
             dst[t][e] = ok ? p * (dp[e] - sD[qi]) : 0.f;
           }
@@ -950,7 +962,8 @@ extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32
   }
   const int nw = pick_warps(seq);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-  const int cap = nw <= 5 ? 3 : 2;
+  // residency is register-bound (128 regs/thread): 4 CTAs of 4 warps (L <= 64), 3 of 5, 2 of 8
+  const int cap = nw <= 4 ? 4 : (nw <= 5 ? 3 : 2);
   if (per_sm > cap) per_sm = cap;
   if (per_sm < 1) per_sm = 1;
   int grid = num_sms() * per_sm;
@@ -990,7 +1003,8 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
                          static_cast<size_t>(nw) * 16 * LDS) * 2 + static_cast<size_t>(lp) * sizeof(float);
     const int items = batch * heads;
     int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-    if (per_sm > 2) per_sm = 2;
+    const int reg_cap = nw <= 4 ? 3 : 2;  // ~168 regs/thread: three 4-warp CTAs (L <= 64) or two 5-warp CTAs fit 64K regs
+    if (per_sm > reg_cap) per_sm = reg_cap;
     int grid = num_sms() * per_sm;
     if (grid > items) grid = items;
     auto st = static_cast<cudaStream_t>(stream);
@@ -1015,7 +1029,14 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   const int nst = (2 * stage_bytes + extra <= 113 * 1024) ? 2 : 1;
   const size_t smem = nst * stage_bytes + extra;
   const int items = batch * heads;
-  if (smem > 227 * 1024) {  // two passes: dQ with K,V resident, then dK/dV with Q,dO resident; D from dO o O
+  // The two-pass path is also the faster one well below the smem limit (B200, B=256 L=197 H=12: 1344 us vs 1659 us
+  // for the single-kernel recompute schedule), so it is the default from L = 192 up. CLIPN_ATTN_BWD_TWO_PASS_MIN moves it.
+  static const int two_pass_min_seq = [] {
+    const char* e = getenv("CLIPN_ATTN_BWD_TWO_PASS_MIN");
+    return e != nullptr ? atoi(e) : 192;
+  }();
+  if (smem > 227 * 1024 || (seq >= two_pass_min_seq && out != nullptr)) {
+    // two passes: dQ with K,V resident, then dK/dV with Q,dO resident; D from dO o O
     CLIPN_REQUIRE(out != nullptr, "attention_bwd: the long-sequence path needs the forward output");
     const size_t smem_dq = (static_cast<size_t>(2) * Lp + 8 * 32) * LDS * 2 + 8 * 16 * sizeof(float);
     const size_t smem_dkv = (static_cast<size_t>(2) * Lp + 8 * 32) * LDS * 2 + static_cast<size_t>(2) * Lp * sizeof(float);

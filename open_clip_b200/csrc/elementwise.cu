@@ -126,25 +126,37 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
        row += static_cast<int64_t>(gridDim.x) * wpb) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + row * d);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + row * d);
+    const uint4* rr = dx_resid ? reinterpret_cast<const uint4*>(dx_resid + row * d) : nullptr;
+    // all three streams (x, dy, residual gradient) are requested up front: 9 independent 16-byte loads per lane
+    uint4 xq[NCH], dq[NCH], rq[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int ci = lane + c * 32;
+      if (ci < nchunk) {
+        xq[c] = xr[ci];
+        dq[c] = dyr[ci];
+        rq[c] = rr ? rr[ci] : make_uint4(0, 0, 0, 0);
+      }
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NCH][8], g[NCH][8];
+    // the rows stay packed (bf16) in registers between the two passes; xhat and g are re-derived, not kept in fp32
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
         float xv[8], dv[8];
-        unpack_bf16x8(xr[ci], xv);
-        unpack_bf16x8(dyr[ci], dv);
+        unpack_bf16x8(xq[c], xv);
+        unpack_bf16x8(dq[c], dv);
         const float4 g0 = reinterpret_cast<const float4*>(gamma)[ci * 2], g1 = reinterpret_cast<const float4*>(gamma)[ci * 2 + 1];
         const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[c][j] = (xv[j] - mean) * rstd;
-          g[c][j] = dv[j] * gm[j];
-          s1 += g[c][j];
-          s2 += g[c][j] * xh[c][j];
-          acc_dg[c][j] += dv[j] * xh[c][j];
+          const float xh = (xv[j] - mean) * rstd;
+          const float gj = dv[j] * gm[j];
+          s1 += gj;
+          s2 += gj * xh;
+          acc_dg[c][j] += dv[j] * xh;
           acc_db[c][j] += dv[j];
         }
       }
@@ -152,20 +164,18 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
     s1 = warp_sum(s1) / d;
     s2 = warp_sum(s2) / d;
     uint4* dxr = reinterpret_cast<uint4*>(dx + row * d);
-    const uint4* rr = dx_resid ? reinterpret_cast<const uint4*>(dx_resid + row * d) : nullptr;
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       const int ci = lane + c * 32;
       if (ci < nchunk) {
-        float o[8];
+        float xv[8], dv[8], o[8], r[8];
+        unpack_bf16x8(xq[c], xv);
+        unpack_bf16x8(dq[c], dv);
+        unpack_bf16x8(rq[c], r);  // zeros when there is no residual gradient
+        const float4 g0 = reinterpret_cast<const float4*>(gamma)[ci * 2], g1 = reinterpret_cast<const float4*>(gamma)[ci * 2 + 1];
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[c][j] - s1 - xh[c][j] * s2);
-        if (rr) {
-          float r[8];
-          unpack_bf16x8(rr[ci], r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2) + r[j];
         dxr[ci] = pack_bf16x8(o);
       }
     }

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("batch,seq,heads", [(2, 17, 2), (3, 20, 2), (2, 50, 12), (2, 77, 8), (1, 197, 4), (1, 1, 1),
+                                             (2, 130, 2),  # 80 < L < 192: the single-kernel recompute backward
                                              # long sequences: two-pass K,V-resident backward (L > 384), Q-streaming
                                              # forward (L > 528); 577 = ViT-L/14-336, 640 = the supported maximum
                                              (1, 400, 2), (2, 577, 3), (1, 640, 1)])

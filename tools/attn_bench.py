@@ -1,4 +1,4 @@
-"""Time the attention kernels alone: python tools/attn_bench.py B L H [causal]  (CUDA events, L2-sized inputs)."""
+"""Time the attention kernels alone: python tools/attn_bench.py B L H [causal] [B L H causal ...]  (CUDA events)."""
 import sys
 
 import torch
@@ -7,8 +7,15 @@ from open_clip_b200 import ops
 
 
 def main():
-    B, Lq, H = (int(a) for a in sys.argv[1:4])
-    causal = len(sys.argv) > 4 and sys.argv[4] == "1"
+    args = sys.argv[1:]
+    if len(args) > 4:  # several configs in one process: groups of four "B L H causal"
+        for i in range(0, len(args), 4):
+            run(int(args[i]), int(args[i + 1]), int(args[i + 2]), args[i + 3] == "1")
+        return
+    run(int(args[0]), int(args[1]), int(args[2]), len(args) > 3 and args[3] == "1")
+
+
+def run(B, Lq, H, causal):
     d = H * 64
     qkv = (torch.randn(B * Lq, 3 * d, device="cuda") * 0.5).to(torch.bfloat16)
     do = (torch.randn(B * Lq, d, device="cuda") * 0.1).to(torch.bfloat16)
