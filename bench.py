@@ -131,6 +131,14 @@ def run_cpu_reference(steps: int, warmup: int, batch: int = 32):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def workload_config(model, batch, world):
+    """The `config` object of the JSON line — identical for the native and the reference arm."""
+    return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, local_loss"
+                        + (" + gather_with_grad fused into the logits GEMM" if world > 1 else " only"),
+            "global_batch": world * batch, "parallelism": f"dp{world}", "optimizer": "AdamW fused (torch)",
+            "cache": "inputs (1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,7 +165,9 @@ def main():
             "impl": "reference", "metric": "image-text pairs/sec (full train step)", "value": r["value"],
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ViT-B-32 / 77-tok text, batch 32, 224^2 synthetic, 1 rank CPU (reference train step)"},
+            # same workload as the native arm (one full train step of the named model; pairs/s); each CPU step is the
+            # bounded sample described in cpu_baseline.sample (batch 32, fp32 — the reference's CPU-runnable config 0)
+            "config": workload_config(args.model, args.batch, max(1, args.gpus)),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -323,10 +333,7 @@ def main():
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.model} bf16, local batch {B}, {world}xB200, local_loss"
-                                   + (" + gather_with_grad fused into the logits GEMM" if world > 1 else " only"),
-                       "global_batch": world * B, "parallelism": f"dp{world}", "optimizer": "AdamW fused (torch)",
-                       "cache": "inputs (1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"},
+            "config": workload_config(args.model, B, world),
             "roofline": {"bound": "tensor", "kernel": top_name,
                          "share_of_step": (sig_time[top] / args.steps) / ms_step if top else None,
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",

@@ -1,16 +1,22 @@
 // Attention core for the CLIP towers (F.scaled_dot_product_attention, transformer.py:223-228), head_dim 64.
 //
-// Sequences are short (50 / 77 / 197 tokens) and the op is 1.6 % of the step's FLOPs: it is HBM-bound, so the
-// design goal is bytes in flight, not tensor throughput.  Persistent CTAs loop over (batch, head) work items with
+// Sequences are short (50 / 77 / 197 tokens; 577 for ViT-L/14-336) and the op is 1.6 % of the step's FLOPs: the
+// bound is HBM bytes, the practical limit is instruction issue and latency (ncu, profiles/), so the design goals
+// are bytes in flight and few non-MMA instructions.  Persistent CTAs loop over (batch, head) work items with
 // a 2-stage cp.async pipeline: while the warps compute item i out of shared memory, the 16-byte cp.async copies
 // of item i+1 (Q, K, V and, in the backward, dO) are already in flight.  Inside an item every warp owns 16-row
 // tiles; S = QK^T and PV run on tensor cores (mma.sync m16n8k16 bf16 -> fp32 — the tiles are 16x64, far below the
 // 128-row tcgen05 atom), softmax is a warp-shuffle (quad) reduction in registers with online rescaling, the
-// causal mask is a predicate (no mask tensor).  Outputs are staged through shared memory and leave as full
-// 128-byte rows.
-// Backward recomputes P from the saved log-sum-exp and uses D_i = sum_j P_ij dP_ij (== rowsum(dO o O)), so the
-// forward output is never re-read: phase 1 (warp = 16 queries) computes D, phase 2a dQ, phase 2b (warp = 16 keys,
-// transposed tiles) dK and dV — no atomics, deterministic.
+// causal mask is a predicate (no mask tensor) evaluated only on key tiles that cross the diagonal or the sequence
+// end.  Outputs are staged through shared memory and leave as full 128-byte rows.
+// Kernels by sequence length:
+//   forward   L <= 528: attention_fwd_kernel (Q,K,V resident)      528 < L <= 640: attention_fwd_long_kernel
+//   backward  L <= 80 : attention_bwd_small_kernel (P, dS cached)   80 < L < 192 : attention_bwd_kernel (recompute)
+//             192 <= L <= 640: attention_bwd_long_dq_kernel + attention_bwd_long_dkv_kernel (two passes)
+// The single-kernel backwards recompute P from the saved log-sum-exp and use D_i = sum_j P_ij dP_ij
+// (== rowsum(dO o O)), so the forward output is not re-read: phase 1 (warp = 16 queries) computes D, phase 2a dQ,
+// phase 2b (warp = 16 keys, transposed tiles) dK and dV — no atomics, deterministic.  The two-pass backward takes
+// D from the forward output instead.
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -61,6 +61,44 @@ def test_single_rank_convention():
     assert comm.clip_grad_convention(False, False, 32, 1) == (1.0 / 64, 1.0, False)
 
 
+def test_grad_checkpointing_schedule(monkeypatch):
+    """set_grad_checkpointing (reference transformer.py:397-402): the forward keeps only each block's input and the
+    backward re-runs block i (saving) right before its backward, from the same input, in reverse order. Kernel
+    launches are replaced by recorders so the schedule itself is checked without a GPU."""
+    from open_clip_b200 import tower
+    calls = []
+
+    def fake_fwd(P, pre, cfg, x, B, ws, save):
+        calls.append(("fwd", pre, save))
+        return x + 1, (("saved", pre, x.clone()) if save else None)
+
+    def fake_bwd(P, G, pre, cfg, s, dx, B, ws):
+        calls.append(("bwd", pre, float(s[2][0])))
+        return dx * 2
+
+    monkeypatch.setattr(tower, "block_forward", fake_fwd)
+    monkeypatch.setattr(tower, "block_backward", fake_bwd)
+    cfg = tower.TowerCfg(width=8, layers=3, heads=1, seq=2, causal=False, prefix="t", embed_dim=4)
+    names = [f"t.resblocks.{i}" for i in range(3)]
+    for ck in (False, True):
+        calls.clear()
+        saved = tower.TowerSaved(batch=1)
+        y = tower._run_blocks(None, cfg, torch.zeros(4), 1, None, saved, ck)
+        assert float(y[0]) == 3.0
+        if ck:
+            assert all(isinstance(b, torch.Tensor) for b in saved.blocks)
+            assert [float(b[0]) for b in saved.blocks] == [0.0, 1.0, 2.0]  # block inputs
+        dx = tower._run_blocks_backward(None, None, cfg, saved, torch.ones(4), 1, None)
+        assert float(dx[0]) == 8.0 and saved.blocks == [None] * 3
+        if not ck:
+            assert calls == [("fwd", n, True) for n in names] + [("bwd", n, float(i)) for i, n in reversed(list(enumerate(names)))]
+        else:
+            want = [("fwd", n, False) for n in names]
+            for i, n in reversed(list(enumerate(names))):
+                want += [("fwd", n, True), ("bwd", n, float(i))]
+            assert calls == want
+
+
 def _gather_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
