@@ -64,6 +64,9 @@ CONFIGS: Dict[str, ClipCfg] = {
     # model_configs/ViT-L-14-336.json
     "ViT-L-14-336": ClipCfg(embed_dim=768, image_size=336, patch_size=14, v_width=1024, v_layers=24,
                             t_width=768, t_heads=12, t_layers=12),
+    # ViT-L-14-336 geometry (patch 14, 577 tokens, width 1024/768) at depth 2+2: reference autograd on CPU in seconds
+    "ViT-L-14-336-d2": ClipCfg(embed_dim=768, image_size=336, patch_size=14, v_width=1024, v_layers=2,
+                               t_width=768, t_heads=12, t_layers=2),
     # small shape-compatible config for fast fixtures (head_dim stays 64 like every native ViT)
     "tiny": ClipCfg(embed_dim=128, image_size=64, patch_size=16, v_width=128, v_layers=2,
                     t_ctx=20, t_vocab=512, t_width=128, t_heads=2, t_layers=2),

@@ -8,8 +8,9 @@ GPU box):
 What it does
   1. imports open_clip from /root/reference/src (with a 2-line `ftfy` stub, the only
      missing hard dependency: src/open_clip/tokenizer.py:14);
-  2. for `tiny` and `ViT-B-32`, fp32 and --precision bf16: loads oracle.init_params() into
-     the reference CLIP, runs reference forward + reference ClipLoss + backward, and
+  2. for `tiny`, `ViT-B-32`, the ViT-L-14-336 geometry at depth 2+2 (ClipLoss) and ViT-B-16 with
+     the reference SigLipLoss, fp32 and --precision bf16: loads oracle.init_params() into
+     the reference CLIP, runs reference forward + reference loss + backward, and
      asserts the oracle restatement reproduces features / loss / every parameter gradient;
   3. runs the reference ClipLoss / SigLipLoss under a real gloo process group (W=2,4) and
      asserts the process-group-free restatement in clip_oracle reproduces values and
@@ -65,27 +66,37 @@ def grad_probe(name: str, g: torch.Tensor):
     return torch.tensor([g.norm().item(), (g * d).sum().item()])
 
 
-def model_goldens(open_clip, cfg_name, batch, seed, precisions=("fp32", "bf16"), keep_full_grads=False):
+def model_goldens(open_clip, cfg_name, batch, seed, precisions=("fp32", "bf16"), keep_full_grads=False,
+                  siglip=False):
+    """siglip=True: reference SigLipLoss (world 1) on a model built with init_logit_scale=log(10),
+    init_logit_bias=-10 (the reference's SigLIP defaults, model.py:326 / factory --siglip)."""
     from oracle import clip_oracle as O
-    from open_clip.loss import ClipLoss
+    from open_clip.loss import ClipLoss, SigLipLoss
     cfg = O.CONFIGS[cfg_name]
-    base = O.init_params(cfg, seed=seed, bias_std=0.02)
+    init_kw = dict(init_logit_scale=2.302585, init_logit_bias=-10.0) if siglip else {}
+    base = O.init_params(cfg, seed=seed, bias_std=0.02, **init_kw)
     image, text = O.synthetic_batch(cfg, batch, seed=100 + seed)
     out = {"cfg": cfg_name, "batch": batch, "seed": seed, "image": image if cfg_name == "tiny" else None,
            "text": text, "param_checksum": float(sum(v.double().abs().sum() for v in base.values())),
-           "image_checksum": float(image.double().abs().sum())}
+           "image_checksum": float(image.double().abs().sum()), "siglip": siglip, "init_kw": init_kw}
     for prec in precisions:
         model = _ref_model(open_clip, cfg, base, prec)
         in_dtype = torch.bfloat16 if prec == "bf16" else torch.float32
         ref = model(image=image.to(in_dtype), text=text)
-        loss = ClipLoss()(ref["image_features"], ref["text_features"], ref["logit_scale"])
+        if siglip:
+            loss = SigLipLoss()(ref["image_features"], ref["text_features"], ref["logit_scale"], ref["logit_bias"])
+        else:
+            loss = ClipLoss()(ref["image_features"], ref["text_features"], ref["logit_scale"])
         loss.backward()
         ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
 
         # ---- pin the oracle restatement to the reference
         p = {k: v.requires_grad_(True) for k, v in O.cast_params(base, prec).items()}
         o = O.clip_forward(p, cfg, image.to(in_dtype), text)
-        oloss = O.clip_loss(o["image_features"], o["text_features"], o["logit_scale"])
+        if siglip:
+            oloss = O.siglip_block_loss(o["image_features"], o["text_features"], o["logit_scale"], o["logit_bias"])
+        else:
+            oloss = O.clip_loss(o["image_features"], o["text_features"], o["logit_scale"])
         oloss.backward()
         tol = 0.0 if prec == "fp32" else 0.0
         for key in ("image_features", "text_features"):
@@ -190,7 +201,7 @@ def main():
     open_clip = _import_reference()
     gold_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold_dir, exist_ok=True)
-    only = sys.argv[1:] or ["tiny", "vitb32", "loss"]
+    only = sys.argv[1:] or ["tiny", "vitb32", "vitl14", "vitb16_siglip", "loss"]
     if "tiny" in only:
         print("model goldens: tiny")
         torch.save(model_goldens(open_clip, "tiny", batch=8, seed=1, keep_full_grads=False),
@@ -198,6 +209,14 @@ def main():
     if "vitb32" in only:
         print("model goldens: ViT-B-32")
         torch.save(model_goldens(open_clip, "ViT-B-32", batch=8, seed=0), os.path.join(gold_dir, "vitb32_model.pt"))
+    if "vitl14" in only:
+        print("model goldens: ViT-L-14-336 geometry, depth 2+2")
+        torch.save(model_goldens(open_clip, "ViT-L-14-336-d2", batch=8, seed=11),
+                   os.path.join(gold_dir, "vitl14_336_d2_model.pt"))
+    if "vitb16_siglip" in only:
+        print("model goldens: ViT-B-16 + SigLipLoss")
+        torch.save(model_goldens(open_clip, "ViT-B-16", batch=8, seed=3, siglip=True),
+                   os.path.join(gold_dir, "vitb16_siglip_model.pt"))
     for w in ((2, 4) if "loss" in only else ()):
         print(f"loss goldens: world={w}")
         torch.save(loss_goldens(w), os.path.join(gold_dir, f"loss_w{w}.pt"))

@@ -55,6 +55,29 @@ def test_vitb32_fp32_features_match_reference_fixture(golden_dir):
     assert abs(float(loss) - g["loss"]) <= 1e-5
 
 
+@pytest.mark.parametrize("fixture,cfg_name", [("vitl14_336_d2_model.pt", "ViT-L-14-336-d2"),
+                                              ("vitb16_siglip_model.pt", "ViT-B-16")])
+def test_other_baseline_geometries_match_reference_fixture(golden_dir, fixture, cfg_name):
+    """BASELINE config 4 geometry (patch 14, 577 tokens, widths 1024/768; depth 2+2) with ClipLoss and config 5
+    (ViT-B-16, 197 tokens) with the reference SigLipLoss: oracle vs the reference's fp32 outputs."""
+    gold = _load(golden_dir, fixture)
+    cfg = O.CONFIGS[cfg_name]
+    base = O.init_params(cfg, seed=gold["seed"], bias_std=0.02, **gold["init_kw"])
+    assert abs(float(sum(v.double().abs().sum() for v in base.values())) - gold["param_checksum"]) < 1e-6 * gold["param_checksum"]
+    image, text = O.synthetic_batch(cfg, gold["batch"], seed=100 + gold["seed"])
+    assert abs(float(image.double().abs().sum()) - gold["image_checksum"]) < 1e-6 * gold["image_checksum"]
+    with torch.no_grad():
+        out = O.clip_forward(base, cfg, image, text)
+        if gold["siglip"]:
+            loss = O.siglip_block_loss(out["image_features"], out["text_features"], out["logit_scale"], out["logit_bias"])
+        else:
+            loss = O.clip_loss(out["image_features"], out["text_features"], out["logit_scale"])
+    g = gold["fp32"]
+    assert (out["image_features"] - g["image_features"]).abs().max() <= 1e-5
+    assert (out["text_features"] - g["text_features"]).abs().max() <= 1e-5
+    assert abs(float(loss) - g["loss"]) <= 1e-5 * max(1.0, abs(g["loss"]))
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_multi_rank_losses_match_gloo_reference_fixture(golden_dir, world):
     gold = _load(golden_dir, f"loss_w{world}.pt")
