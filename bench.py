@@ -131,6 +131,21 @@ def run_cpu_reference(steps: int, warmup: int, batch: int = 32):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def logits_gemm_roofline(sig_time, sig_count, peak_tflops):
+    """BASELINE.json's second figure: the fused gather + logits + log-sum-exp GEMMs of the loss forward.
+    sig_time / sig_count map a GEMM signature (M, N, K, epilogue, a_mn, b_mn) to total ms / launches; the loss
+    forward is the signature with the LSE epilogue (6). Returns None when no such launch was timed."""
+    lse_sigs = [s for s in sig_time if s[3] == 6]
+    n = sum(sig_count[s] for s in lse_sigs)
+    ms = sum(sig_time[s] for s in lse_sigs)
+    if n == 0 or ms <= 0:
+        return None
+    tf = sum(2.0 * s[0] * s[1] * s[2] * sig_count[s] for s in lse_sigs) / (ms * 1e-3) / 1e12
+    return {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,LSE> (peer-read logits GEMM + row LSE) + lse_combine",
+            "achieved": tf, "peak": peak_tflops, "unit": "TFLOP/s", "frac": tf / peak_tflops, "launches_timed": n,
+            "avg_launch_ms": ms / n, "shape_mnk": [list(s[:3]) for s in lse_sigs]}
+
+
 def workload_config(model, batch, world):
     """The `config` object of the JSON line — identical for the native and the reference arm."""
     return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, local_loss"
@@ -329,6 +344,7 @@ def main():
         traffic = None
         if top and (top[3], top[1], top[2]) in ncu_traffic_m51200:
             traffic = ncu_traffic_m51200[(top[3], top[1], top[2])] * top[0] / 51200.0
+        logits_roofline = logits_gemm_roofline(sig_time, sig_count, peaks["bf16_sustained"])
         out = {
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -351,6 +367,7 @@ def main():
                               "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                               "frac": pairs_per_s / world * STEP_GFLOP_PER_PAIR / 1e3 / peaks["bf16_sustained"],
                               "flops_per_pair": STEP_GFLOP_PER_PAIR * 1e9},
+            "roofline_logits_gemm": logits_roofline,
             "gpu_launches": launches,
             "clocks": clocks,
             "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),

@@ -279,8 +279,15 @@ def clip_lse_fwd(rows: torch.Tensor, col_ptrs: Sequence[int], scale: torch.Tenso
     ws = torch.empty(L.lib().clipn_clip_lse_workspace(b, world * b), dtype=F32, device=rows.device)
     lse = torch.empty(b, dtype=F32, device=rows.device)
     pos = torch.zeros(b, dtype=F32, device=rows.device)
+    prof = PROFILE_KEY == "all"
+    if prof:  # bench.py: the fused gather + logits + LSE GEMM (and its tiny combine kernel) as one timed signature
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     _call(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
                                        label_offset, lse.data_ptr(), pos.data_ptr(), ws.data_ptr(), _stream()))
+    if prof:
+        e1.record()
+        PROFILE_EVENTS.append((e0, e1, (b, world * b, e, L.EPI_LSE, False, False)))
     return lse, pos
 
 

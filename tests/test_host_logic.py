@@ -61,6 +61,23 @@ def test_single_rank_convention():
     assert comm.clip_grad_convention(False, False, 32, 1) == (1.0 / 64, 1.0, False)
 
 
+def test_bench_helpers_aggregate_without_a_gpu():
+    """bench.py's JSON helpers are pure functions: the logits-GEMM roofline aggregates only LSE-epilogue signatures
+    (2*M*N*K per launch over the summed CUDA-event time) and both arms print the same `config`."""
+    import json
+    import bench
+    lse, gelu = (4096, 32768, 512, 6, False, False), (204800, 3072, 768, 9, False, False)
+    r = bench.logits_gemm_roofline({lse: 3.2, gelu: 30.0}, {lse: 16, gelu: 96}, 1461.6)
+    want = 2.0 * 4096 * 32768 * 512 * 16 / 3.2e-3 / 1e12
+    assert abs(r["achieved"] - want) < 1e-6 * want and abs(r["frac"] - want / 1461.6) < 1e-9
+    assert r["launches_timed"] == 16 and abs(r["avg_launch_ms"] - 0.2) < 1e-12 and r["shape_mnk"] == [[4096, 32768, 512]]
+    assert bench.logits_gemm_roofline({gelu: 30.0}, {gelu: 96}, 1461.6) is None
+    json.dumps(r)
+    c1, c8 = bench.workload_config("ViT-B-32", 4096, 1), bench.workload_config("ViT-B-32", 4096, 8)
+    assert "local batch 4096, 1xB200" in c1["workload"] and c1["global_batch"] == 4096
+    assert c8["global_batch"] == 32768 and c8["parallelism"] == "dp8" and "gather" in c8["workload"]
+
+
 def test_grad_checkpointing_schedule(monkeypatch):
     """set_grad_checkpointing (reference transformer.py:397-402): the forward keeps only each block's input and the
     backward re-runs block i (saving) right before its backward, from the same input, in reverse order. Kernel
