@@ -40,10 +40,35 @@ class _VisualNode(_Node):
     def no_weight_decay(self):
         return {"positional_embedding", "class_embedding"}  # transformer.py:778-781
 
+    def layer_groups(self, pooler_in_head: bool = True):
+        """Input -> output partition shared by lock() and layer-wise LR decay (transformer.py:718-743):
+        embeddings | layer.i (last block together with ln_post) | proj."""
+        groups = [("embeddings", [self.conv1, self.class_embedding, self.positional_embedding, self.ln_pre])]
+        blocks = list(self.transformer.resblocks)
+        for i, blk in enumerate(blocks):
+            groups.append((f"layer.{i}", [blk, self.ln_post] if i == len(blocks) - 1 else [blk]))
+        groups.append(("proj", [self.proj]))
+        return groups
+
+    def lock(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
+        _lock_groups(self.layer_groups(), unlocked_groups)  # transformer.py:745-753
+
+
+def _lock_groups(groups, unlocked: int):
+    """Freeze bottom-up, leave the top `unlocked` groups trainable; every group is set explicitly so repeated calls
+    with different counts are idempotent (transformer.py:2044-2054)."""
+    n_freeze = len(groups) if not unlocked else len(groups) - unlocked
+    for i, (_, members) in enumerate(groups):
+        for m in members:
+            for p in ([m] if isinstance(m, nn.Parameter) else m.parameters()):
+                p.requires_grad = i >= n_freeze
+
 
 def _block_node(d: int, mlp: int) -> _Node:
     b = _Node()
-    b.ln_1, b.ln_2, b.attn, b.mlp = _Node(), _Node(), _Node(), _Node()
+    # registration order = the reference's (ln_1, attn, ln_2, mlp): named_parameters() order is what index-based
+    # optimizer checkpoints and DDP buckets follow
+    b.ln_1, b.attn, b.ln_2, b.mlp = _Node(), _Node(), _Node(), _Node()
     b.attn.out_proj, b.mlp.c_fc, b.mlp.c_proj = _Node(), _Node(), _Node()
     for ln in (b.ln_1, b.ln_2):
         ln.weight = nn.Parameter(torch.ones(d))
@@ -136,11 +161,13 @@ class NativeCLIP(nn.Module):
         self.visual.conv1.weight = nn.Parameter(torch.empty(vw, 3, v["patch_size"], v["patch_size"]))
         self.visual.class_embedding = nn.Parameter(torch.empty(vw))
         self.visual.positional_embedding = nn.Parameter(torch.empty(grid * grid + 1, vw))
-        self.visual.ln_pre, self.visual.ln_post = _Node(), _Node()
+        # submodule order as in the reference: conv1, ln_pre, transformer, ln_post (named_parameters() order)
+        self.visual.ln_pre = _Node()
+        self.visual.transformer = _transformer_node(vw, v["layers"], mlp_ratio)
+        self.visual.ln_post = _Node()
         for ln in (self.visual.ln_pre, self.visual.ln_post):
             ln.weight = nn.Parameter(torch.ones(vw))
             ln.bias = nn.Parameter(torch.zeros(vw))
-        self.visual.transformer = _transformer_node(vw, v["layers"], mlp_ratio)
         self.visual.proj = nn.Parameter(torch.empty(vw, embed_dim))
         self.transformer = _transformer_node(tw, t["layers"], t.get("mlp_ratio", 4.0))
         self.token_embedding = _Node()
@@ -238,13 +265,20 @@ class NativeCLIP(nn.Module):
         self.grad_checkpointing = enable
 
     def lock_image_tower(self, unlocked_groups: int = 0, freeze_bn_stats: bool = False):
-        for n, p in self.named_parameters():
-            if n.startswith("visual."):
-                p.requires_grad = False
+        # model.py:368-370 -> VisionTransformer.lock: unlocked_groups counts the top groups (proj first) left trainable
+        self.visual.lock(unlocked_groups=unlocked_groups, freeze_bn_stats=freeze_bn_stats)
+
+    def text_layer_groups(self, pooler_in_head: bool = True):
+        """embeddings | layer.i (last block together with ln_final) | proj (transformer.py:1999-2031)."""
+        groups = [("embeddings", [self.token_embedding, self.positional_embedding])]
+        blocks = list(self.transformer.resblocks)
+        for i, blk in enumerate(blocks):
+            groups.append((f"layer.{i}", [blk, self.ln_final] if i == len(blocks) - 1 else [blk]))
+        groups.append(("proj", [self.text_projection]))
+        return groups
 
     def lock_text_tower(self, unlocked_layers: int = 0, freeze_layer_norm: bool = True, pooler_in_head: bool = True):
-        for n in self._tower_param_names["text"]:
-            dict(self.named_parameters())[n].requires_grad = False
+        _lock_groups(self.text_layer_groups(pooler_in_head), unlocked_layers)  # transformer.py:2056-2076
 
     def no_weight_decay(self):
         # model.py:381-387

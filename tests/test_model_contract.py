@@ -1,0 +1,134 @@
+"""CPU suite: the drop-in boundary of NativeCLIP that does not need a kernel launch — parameter
+names/shapes/dtypes, the attributes and methods the reference's task/optimizer/main code touches, and the
+"no CPU fallback" rule. Where /root/reference is present (authoring container only) the parameter table is also
+compared with the real reference CLIP."""
+import os
+import sys
+
+import pytest
+import torch
+
+from open_clip_b200._lib import ClipnError
+from open_clip_b200.loss import NativeClipLoss, NativeSigLipLoss
+from open_clip_b200.model import CONFIGS, NativeCLIP, create_model
+from oracle import clip_oracle as O
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _small(name):
+    """The named geometry with one block per tower (parameter contract only; keeps the CPU suite fast)."""
+    c = CONFIGS[name]
+    v, t = dict(c["vision_cfg"], layers=1), dict(c["text_cfg"], layers=1)
+    return NativeCLIP(c["embed_dim"], v, t, output_dict=True, device="cpu"), O.ClipCfg(
+        embed_dim=c["embed_dim"], image_size=v["image_size"], patch_size=v["patch_size"], v_width=v["width"], v_layers=1,
+        t_ctx=t["context_length"], t_vocab=t["vocab_size"], t_width=t["width"], t_heads=t["heads"], t_layers=1)
+
+
+@pytest.mark.parametrize("name", ["ViT-B-32", "ViT-B-16", "ViT-L-14-336", "tiny"])
+def test_parameter_names_shapes_dtypes(name):
+    m, cfg = _small(name)
+    shapes = O.param_shapes(cfg)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(shapes[k]), k
+        assert v.dtype == (BF16 if O.is_lowp_param(k) else F32), k  # convert_weights_to_lp contract (model.py:738-765)
+    assert all(isinstance(p, torch.nn.Parameter) for p in m.parameters())
+    assert m.visual.image_size == (cfg.image_size, cfg.image_size)
+    assert m.context_length == cfg.t_ctx and m.vocab_size == cfg.t_vocab
+    assert isinstance(m.logit_scale, torch.nn.Parameter) and m.logit_scale.ndim == 0
+    assert "attn_mask" not in sd  # non-persistent buffer, as in the reference (model.py:360)
+
+
+def test_full_vitb32_parameter_count_and_optimizer_grouping_inputs():
+    m = create_model("ViT-B-32", device="cpu")
+    assert sum(p.numel() for p in m.parameters()) == 151277313
+    assert m.no_weight_decay() == {"positional_embedding", "visual.positional_embedding", "visual.class_embedding"}
+    # optim.py:67-75 splits weight decay by ndim: every gain/bias must stay <= 1-D, every matrix >= 2-D
+    for n, p in m.named_parameters():
+        if n.endswith(".bias") or ".ln_" in n or n.startswith(("ln_final", "visual.ln_")) or n == "logit_scale":
+            assert p.ndim <= 1, n
+        if n.endswith("in_proj_weight") or n.endswith("c_fc.weight") or n == "visual.conv1.weight":
+            assert p.ndim >= 2, n
+
+
+def test_no_cpu_fallback_and_loss_requires_cuda():
+    m, cfg = _small("tiny")
+    image, text = O.synthetic_batch(cfg, 2, seed=0)
+    with pytest.raises(ClipnError):
+        m(image=image.to(BF16), text=text)
+    with pytest.raises(ClipnError):
+        m.encode_text(text)
+    f = torch.nn.functional.normalize(torch.randn(8, 16), dim=-1).to(BF16)
+    with pytest.raises((ClipnError, RuntimeError, AssertionError)):
+        NativeClipLoss()(f, f, torch.tensor(10.0))
+    with pytest.raises((ClipnError, RuntimeError, AssertionError)):
+        NativeSigLipLoss()(f, f, torch.tensor(10.0), torch.tensor(-10.0))
+
+
+def test_lock_towers_follow_reference_group_semantics():
+    """lock_image_tower / lock_text_tower (main.py:315-326): unlocked_* counts the TOP groups left trainable, proj
+    first, the last block travels with ln_post / ln_final; every call sets all groups explicitly."""
+    c = CONFIGS["tiny"]
+    m = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], device="cpu")
+    names = [n for n, _ in m.visual.layer_groups()]
+    assert names == ["embeddings", "layer.0", "layer.1", "proj"]
+    m.lock_image_tower(unlocked_groups=0)
+    assert not any(p.requires_grad for n, p in m.named_parameters() if n.startswith("visual."))
+    assert all(p.requires_grad for n, p in m.named_parameters() if not n.startswith("visual."))
+    m.lock_image_tower(unlocked_groups=2)  # proj + (last block, ln_post)
+    on = {n for n, p in m.named_parameters() if n.startswith("visual.") and p.requires_grad}
+    assert "visual.proj" in on and "visual.ln_post.weight" in on
+    assert any(n.startswith("visual.transformer.resblocks.1.") for n in on)
+    assert not any(n.startswith("visual.transformer.resblocks.0.") for n in on)
+    assert "visual.conv1.weight" not in on and "visual.ln_pre.weight" not in on
+    m.lock_text_tower(unlocked_layers=1)  # only text_projection stays trainable
+    text_on = {n for n, p in m.named_parameters() if not n.startswith("visual.") and p.requires_grad}
+    assert text_on == {"text_projection", "logit_scale"}
+    m.lock_text_tower(unlocked_layers=0)
+    assert not m.text_projection.requires_grad and not m.ln_final.weight.requires_grad
+    assert [n for n, _ in m.text_layer_groups()] == ["embeddings", "layer.0", "layer.1", "proj"]
+
+
+def test_state_dict_round_trip_from_reference_layout_and_siglip_bias():
+    c = CONFIGS["tiny"]
+    cfg = O.CONFIGS["tiny"]
+    base = O.init_params(cfg, seed=5, bias_std=0.02, init_logit_scale=2.302585, init_logit_bias=-10.0)
+    m = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], init_logit_bias=-10.0, device="cpu")
+    m.load_reference_state_dict(base)
+    for k, v in m.state_dict().items():
+        want = base[k].to(v.dtype)
+        assert torch.equal(v, want), k
+    assert "logit_bias" in m.state_dict() and float(m.logit_bias) == -10.0
+    with pytest.raises(ClipnError):
+        m.load_reference_state_dict({k: v for k, v in base.items() if k != "ln_final.weight"})
+    m.set_grad_checkpointing(True)
+    assert m.grad_checkpointing is True
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="authoring container only")
+def test_parameter_table_equals_the_real_reference_clip():
+    import tempfile
+    stub = tempfile.mkdtemp(prefix="ftfy_stub_")
+    with open(os.path.join(stub, "ftfy.py"), "w") as f:
+        f.write("def fix_text(s):\n    return s\n")
+    sys.path[:0] = [stub, "/root/reference/src"]
+    try:
+        from open_clip.model import CLIP, convert_weights_to_lp
+        c = CONFIGS["ViT-B-32"]
+        ref = CLIP(c["embed_dim"], dict(c["vision_cfg"], layers=2), dict(c["text_cfg"], layers=2), output_dict=True)
+        convert_weights_to_lp(ref, dtype=torch.bfloat16)
+        mine = NativeCLIP(c["embed_dim"], dict(c["vision_cfg"], layers=2), dict(c["text_cfg"], layers=2), device="cpu")
+        rs, ms = ref.state_dict(), mine.state_dict()
+        assert list(rs) == list(ms)  # same names in the same order
+        for k in rs:
+            assert rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype, k
+        assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
+        assert [n for n, _ in ref.visual.layer_groups()] == [n for n, _ in mine.visual.layer_groups()]
+    finally:
+        del sys.path[:2]
+        for k in [k for k in sys.modules if k == "ftfy" or k.startswith("open_clip")]:
+            if k.startswith("open_clip_b200"):
+                continue
+            del sys.modules[k]
