@@ -126,6 +126,15 @@ def test_parameter_table_equals_the_real_reference_clip():
             assert rs[k].shape == ms[k].shape and rs[k].dtype == ms[k].dtype, k
         assert [n for n, _ in ref.named_parameters()] == [n for n, _ in mine.named_parameters()]
         assert [n for n, _ in ref.visual.layer_groups()] == [n for n, _ in mine.visual.layer_groups()]
+        # loss plug points: same constructor and forward parameters, same defaults (loss.py:59-66,118; :324-331,406)
+        import inspect
+        from open_clip.loss import ClipLoss, SigLipLoss
+        for r, mn in ((ClipLoss, NativeClipLoss), (SigLipLoss, NativeSigLipLoss)):
+            for fn in ("__init__", "forward"):
+                pr = inspect.signature(getattr(r, fn)).parameters
+                pm = inspect.signature(getattr(mn, fn)).parameters
+                assert list(pr) == list(pm), (r.__name__, fn)
+                assert [p.default for p in pr.values()] == [p.default for p in pm.values()], (r.__name__, fn)
     finally:
         del sys.path[:2]
         for k in [k for k in sys.modules if k == "ftfy" or k.startswith("open_clip")]:
