@@ -108,6 +108,67 @@ def test_state_dict_round_trip_from_reference_layout_and_siglip_bias():
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="authoring container only")
+def test_reference_task_optimizer_and_train_step_drive_the_native_objects(monkeypatch):
+    """The reference's OWN CLIPTask, create_optimizer and train-step closure (clip_task.py:28-46, optim.py:336,
+    train.py:163-185, image_text_task.py:91-101) operate on NativeCLIP + NativeClipLoss unchanged. The two kernel
+    entry points (tower forward, loss forward) are replaced by the oracle's CPU math, so what is exercised is the
+    plumbing: keyword names, dict keys, parameter discovery, weight-decay grouping, in-place logit_scale clamp."""
+    import tempfile
+    stub = tempfile.mkdtemp(prefix="ftfy_stub_")
+    with open(os.path.join(stub, "ftfy.py"), "w") as f:
+        f.write("def fix_text(s):\n    return s\n")
+    sys.path[:0] = [stub, "/root/reference/src"]
+    try:
+        from contextlib import nullcontext
+        from types import SimpleNamespace
+        from open_clip.task.clip_task import CLIPTask
+        from open_clip_train.optim import OptimizerCfg, create_optimizer
+        from open_clip_train.train import _make_train_step_no_accum_no_scaler
+        c, cfg = CONFIGS["tiny"], O.CONFIGS["tiny"]
+        model = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], output_dict=True, device="cpu")
+
+        def cpu_tower(self, which, inp, normalize):
+            p = {k: v.float() for k, v in self.named_parameters()}
+            enc = O.encode_image if which == "visual" else O.encode_text
+            return enc(p, cfg, inp.float() if which == "visual" else inp, normalize=normalize)
+
+        def cpu_loss(self, image_features, text_features, logit_scale, logit_bias=None, output_dict=False):
+            loss = O.clip_loss(image_features, text_features, logit_scale)
+            return {"contrastive_loss": loss} if output_dict else loss
+
+        monkeypatch.setattr(NativeCLIP, "_run_tower", cpu_tower)
+        monkeypatch.setattr(NativeClipLoss, "forward", cpu_loss)
+        task = CLIPTask(model, loss=NativeClipLoss(), device=torch.device("cpu"), verbose=False)
+        assert task.trainable_module is model and isinstance(task.loss, NativeClipLoss)
+        opt = create_optimizer(task.trainable_module, OptimizerCfg(lr=1e-3, weight_decay=0.2, beta1=0.9, beta2=0.98, eps=1e-6))
+        decayed = {id(p) for g in opt.param_groups if g["weight_decay"] > 0 for p in g["params"]}
+        named = dict(model.named_parameters())
+        assert id(named["visual.conv1.weight"]) in decayed and id(named["text_projection"]) in decayed
+        for n in ("positional_embedding", "visual.positional_embedding", "visual.class_embedding", "logit_scale",
+                  "ln_final.weight", "visual.transformer.resblocks.0.mlp.c_fc.bias"):
+            assert id(named[n]) not in decayed, n
+        assert sum(len(g["params"]) for g in opt.param_groups) == len(named)
+        step = _make_train_step_no_accum_no_scaler(task, opt, nullcontext, SimpleNamespace(grad_clip_norm=1.0))
+        image, text = O.synthetic_batch(cfg, 8, seed=3)
+        before = {k: v.detach().clone() for k, v in named.items()}
+        task.train()
+        losses, report = step({"image": image, "text": text})
+        assert set(losses) >= {"contrastive_loss", "loss"} and torch.isfinite(losses["loss"])
+        assert "logit_scale" in report
+        assert all(p.grad is not None for p in model.parameters())
+        assert any(not torch.equal(before[k], v) for k, v in named.items())  # optimizer.step() updated our parameters
+        with torch.no_grad():
+            model.logit_scale.fill_(9.0)
+        task.clamp_logit_scale()
+        assert abs(float(model.logit_scale.detach()) - 4.605170185988092) < 1e-6  # ln(100), in place on our Parameter
+    finally:
+        del sys.path[:2]
+        for k in [k for k in sys.modules if k == "ftfy" or k.startswith(("open_clip.", "open_clip_train"))
+                  or k == "open_clip"]:
+            del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="authoring container only")
 def test_parameter_table_equals_the_real_reference_clip():
     import tempfile
     stub = tempfile.mkdtemp(prefix="ftfy_stub_")
