@@ -161,6 +161,24 @@ def test_reference_task_optimizer_and_train_step_drive_the_native_objects(monkey
             model.logit_scale.fill_(9.0)
         task.clamp_logit_scale()
         assert abs(float(model.logit_scale.detach()) - 4.605170185988092) < 1e-6  # ln(100), in place on our Parameter
+
+        # SigLIPTask (siglip_task.py:8-45): same flow, model_out additionally carries logit_bias (model.py:540-541)
+        from open_clip.task.siglip_task import SigLIPTask
+
+        def cpu_siglip(self, image_features, text_features, logit_scale, logit_bias, output_dict=False):
+            loss = O.siglip_block_loss(image_features, text_features, logit_scale, logit_bias)
+            return {"contrastive_loss": loss} if output_dict else loss
+
+        monkeypatch.setattr(NativeSigLipLoss, "forward", cpu_siglip)
+        sig_model = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], init_logit_scale=2.302585,
+                               init_logit_bias=-10.0, output_dict=True, device="cpu")
+        sig_task = SigLIPTask(sig_model, loss=NativeSigLipLoss(), device=torch.device("cpu"), verbose=False)
+        sig_opt = create_optimizer(sig_task.trainable_module, OptimizerCfg(lr=1e-3))
+        sig_step = _make_train_step_no_accum_no_scaler(sig_task, sig_opt, nullcontext, SimpleNamespace())
+        sig_task.train()
+        losses, report = sig_step({"image": image, "text": text})
+        assert torch.isfinite(losses["loss"]) and sig_model.logit_bias.grad is not None
+        assert "logit_bias" in report and "logit_scale" in report
     finally:
         del sys.path[:2]
         for k in [k for k in sys.modules if k == "ftfy" or k.startswith(("open_clip.", "open_clip_train"))
