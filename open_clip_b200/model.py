@@ -111,6 +111,7 @@ class _TowerFn(torch.autograd.Function):
             raise ClipnError("backward through a NativeCLIP tower that ran without saved activations")
         cfg = model._vcfg if which == "visual" else model._tcfg
         arena = model._grad_arena(which)
+        model._unalias_grads(which)
         arena["flat32"].zero_()
         G = arena["views32"]
         bwd = tower.vision_backward if which == "visual" else tower.text_backward
@@ -232,6 +233,28 @@ class NativeCLIP(nn.Module):
         self._scratch = {"visual": tower.Scratch(), "text": tower.Scratch()}
         self._arenas: Dict[str, dict] = {}
         self.grad_checkpointing = False
+
+    @torch.no_grad()
+    def _unalias_grads(self, which: str) -> int:
+        """Gradient accumulation (`--accum-freq`, train.py:236-311; or zero_grad(set_to_none=False)): autograd may keep
+        the arena views this tower returned as the parameters' `.grad` without copying them. Before the arena is
+        zeroed and refilled for the next micro-batch, give every such parameter its own copy, so the earlier
+        micro-batches' sum survives and autograd's `grad += new` adds two different buffers. Returns the number of
+        gradients that were detached (0 on the ordinary zero_grad(set_to_none=True) path)."""
+        a = self._arenas.get(which)
+        if a is None:
+            return 0
+        params = dict(self.named_parameters())
+        n_detached = 0
+        for n in self._tower_param_names[which]:
+            p = params[n]
+            if p.grad is None:
+                continue
+            view = a["views16"].get(n) if p.dtype == BF16 else a["views32"].get(n)
+            if view is not None and p.grad.data_ptr() == view.data_ptr():
+                p.grad = p.grad.clone()
+                n_detached += 1
+        return n_detached
 
     def _grad_arena(self, which: str) -> dict:
         """Flat fp32 gradient accumulators for one tower (low-precision params first) + a bf16 shadow."""

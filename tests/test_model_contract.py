@@ -107,6 +107,30 @@ def test_state_dict_round_trip_from_reference_layout_and_siglip_bias():
     assert m.grad_checkpointing is True
 
 
+def test_accumulated_grads_never_alias_the_gradient_arena():
+    """`--accum-freq` (train.py:236-311) calls backward several times before optimizer.step(). The towers hand autograd
+    views of a flat arena that the next backward zeroes and refills; a `.grad` still pointing into the arena must be
+    given its own storage first, otherwise the earlier micro-batches' gradients are lost."""
+    c = CONFIGS["tiny"]
+    m = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], device="cpu")
+    assert m._unalias_grads("visual") == 0  # no arena yet
+    arena = m._grad_arena("visual")
+    named = dict(m.named_parameters())
+    lowp, highp = "visual.conv1.weight", "visual.ln_pre.weight"
+    arena["views16"][lowp].fill_(0.5)
+    arena["views32"][highp].fill_(2.0)
+    named[lowp].grad = arena["views16"][lowp]          # what autograd does when it keeps the returned tensor
+    named[highp].grad = arena["views32"][highp].detach()
+    named["visual.proj"].grad = torch.ones_like(named["visual.proj"])  # an ordinary, separate gradient
+    assert m._unalias_grads("visual") == 2
+    arena["flat32"].zero_()
+    arena["flat16"].zero_()
+    assert float(named[lowp].grad.float().mean()) == 0.5 and float(named[highp].grad.mean()) == 2.0
+    assert named[lowp].grad.data_ptr() != arena["views16"][lowp].data_ptr()
+    assert named[lowp].grad.dtype == BF16 and named[highp].grad.dtype == F32
+    assert m._unalias_grads("visual") == 0 and m._unalias_grads("text") == 0
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="authoring container only")
 def test_reference_task_optimizer_and_train_step_drive_the_native_objects(monkeypatch):
     """The reference's OWN CLIPTask, create_optimizer and train-step closure (clip_task.py:28-46, optim.py:336,
