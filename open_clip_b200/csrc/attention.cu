@@ -471,7 +471,9 @@ attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16*
 // dV = P^T dO and dK = dS^T Q need no recomputed S^T / dP^T, no exps and no masks: 5 GEMM units instead of 9.
 // (ncu, round 1: the recomputing kernel is issue-bound — 139 M warp instructions, 45 % issue-active, 21 % DRAM.)
 // ------------------------------------------------------------------------------------------------
-template <int NT>
+// PF (experimental, CLIPN_ATTN_BWD_PREFETCH=1): K and V are dead once phase A is done, so the next item's K,V tiles
+// are requested before phase B and land while it runs; only Q and dO are waited for at the top of the next item.
+template <int NT, bool PF>
 __global__ void __launch_bounds__(160, 2)
 attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
                            const float* __restrict__ lse_in, __nv_bfloat16* __restrict__ dqkv,
@@ -494,12 +496,24 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
 
   for (int t = 0; t < 4; ++t) tile_zero_pad(sQ + t * Lp * LDS, seq, Lp);
 
+  auto load_kv = [&](int it) {
+    const __nv_bfloat16* kb = qkv + static_cast<int64_t>(it / heads) * seq * ld + (it % heads) * HD;
+    tile_cp_async(sK, kb + d, ld, seq);
+    tile_cp_async(sV, kb + 2 * d, ld, seq);
+  };
+  if constexpr (PF) {
+    if (static_cast<int>(blockIdx.x) < items) load_kv(blockIdx.x);
+    cp_async_commit();
+  }
+
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int b = item / heads, h = item % heads;
     const __nv_bfloat16* base = qkv + static_cast<int64_t>(b) * seq * ld + h * HD;
     tile_cp_async(sQ, base, ld, seq);
-    tile_cp_async(sK, base + d, ld, seq);
-    tile_cp_async(sV, base + 2 * d, ld, seq);
+    if constexpr (!PF) {
+      tile_cp_async(sK, base + d, ld, seq);
+      tile_cp_async(sV, base + 2 * d, ld, seq);
+    }
     tile_cp_async(sDO, dout + static_cast<int64_t>(b) * seq * d + h * HD, d, seq);
     cp_async_commit();
     for (int i = threadIdx.x; i < Lp; i += blockDim.x)
@@ -575,6 +589,10 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
       if (dbias != nullptr) tile_colsum_atomic(sOut, dbias + h * HD, lane);
     }
     __syncthreads();
+    if constexpr (PF) {  // sK / sV are not read again for this item
+      if (item + static_cast<int>(gridDim.x) < items) load_kv(item + gridDim.x);
+      cp_async_commit();
+    }
 
     // ---------------- phase B: warp owns 16 keys; P^T and dS^T come from shared memory ----------------
     for (int c0 = warp * 16; c0 < Lp; c0 += nwarps * 16) {
@@ -606,6 +624,7 @@ attention_bwd_small_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfl
     }
     __syncthreads();  // tiles, sP/sdS and sLse are rewritten by the next item
   }
+  if constexpr (PF) cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1014,19 +1033,19 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
     int grid = num_sms() * per_sm;
     if (grid > items) grid = items;
     auto st = static_cast<cudaStream_t>(stream);
-    if (lp == 64) {
-      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attention_bwd_small_kernel<8><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                 reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-                                                                 reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, items, seq,
-                                                                 heads, causal, scale);
-    } else {
-      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_bwd_small_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attention_bwd_small_kernel<10><<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                  reinterpret_cast<const __nv_bfloat16*>(dout), lse,
-                                                                  reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, items, seq,
-                                                                  heads, causal, scale);
-    }
+    static const bool prefetch_kv = [] {  // experimental, off by default (not yet measured on hardware)
+      const char* e = getenv("CLIPN_ATTN_BWD_PREFETCH");
+      return e != nullptr && e[0] == '1';
+    }();
+    using SmallKernel = void (*)(const __nv_bfloat16*, const __nv_bfloat16*, const float*, __nv_bfloat16*, float*, int, int,
+                                 int, int, float);
+    SmallKernel kern;
+    if (lp == 64) kern = prefetch_kv ? attention_bwd_small_kernel<8, true> : attention_bwd_small_kernel<8, false>;
+    else kern = prefetch_kv ? attention_bwd_small_kernel<10, true> : attention_bwd_small_kernel<10, false>;
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    kern<<<grid, nw * 32, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
+                                      reinterpret_cast<const __nv_bfloat16*>(dout), lse,
+                                      reinterpret_cast<__nv_bfloat16*>(dqkv), dbias, items, seq, heads, causal, scale);
     CLIPN_CHECK_CUDA(cudaGetLastError());
     return CLIPN_OK;
   }

@@ -621,7 +621,16 @@ __global__ void gemm_ref_kernel(const GemmParams p_in, RefOperands ops, int bn) 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-int gemm_tile_n(int n) { return (n % 256 == 0) ? 256 : 128; }
+int gemm_tile_n(int n) {
+  // CLIPN_GEMM_TILE_N=128 forces the 128-wide tile everywhere (tuning experiments: wave quantisation of the
+  // N = 768 / 512 outputs); the default picks 256 whenever it divides N.
+  static const int forced = [] {
+    const char* e = getenv("CLIPN_GEMM_TILE_N");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  if (forced == 128) return 128;
+  return (n % 256 == 0) ? 256 : 128;
+}
 
 template <int BN, int EPI>
 static int launch_tc(const TmapSet& tm, const GemmParams& p, cudaStream_t stream) {
