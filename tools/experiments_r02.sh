@@ -5,6 +5,8 @@
 mkdir -p gpurun_out
 export PYTHONPATH=.
 {
+  echo "== HBM: write-only vs copy vs read-only (is 3.2 TB/s on the GEMM store path a DRAM limit?)"
+  timeout 120 python tools/hbm_write_bench.py 630
   echo "== attention backward with K/V prefetch: parity first"
   CLIPN_ATTN_BWD_PREFETCH=1 timeout 200 python -m pytest tests/test_gpu_attention.py -x -q -m gpu 2>&1 | tail -3
   echo "== attention timing: default, then prefetch"
