@@ -51,6 +51,33 @@ def test_gemm_desc_layout_matches_header():
     assert names == [f[0] for f in L.GemmDesc._fields_]
 
 
+def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
+    """include/clipn.h must compile as C99 and as C++ with nothing but <stdint.h> (no torch / CUDA types in the
+    boundary), and the byte layout gcc gives `clipn_gemm_desc` must be the one the ctypes binding uses."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    fields = [f[0] for f in L.GemmDesc._fields_]
+    prog = ['#include <stddef.h>', '#include <stdio.h>', '#include "clipn.h"', 'int main(void) {',
+            '  printf("sizeof %zu\\n", sizeof(clipn_gemm_desc));']
+    prog += [f'  printf("{f} %zu\\n", offsetof(clipn_gemm_desc, {f}));' for f in fields]
+    prog += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out.pop("sizeof")) == ctypes.sizeof(L.GemmDesc)
+    for f in fields:
+        assert int(out[f]) == getattr(L.GemmDesc, f).offset, f
+    if shutil.which("g++") is not None:
+        cpp = tmp_path / "hdr.cpp"
+        cpp.write_text('#include "clipn.h"\nint main() { return clipn_version == nullptr; }\n')
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     from open_clip_b200 import ops
