@@ -78,6 +78,36 @@ def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
         subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
 
 
+def test_a_plain_c_program_links_and_calls_the_library(tmp_path):
+    """The boundary is usable without Python or torch: a C translation unit that includes only clipn.h links against
+    libclipn.so and calls it. Without a GPU a compute entry point must come back with an error code and a message,
+    not crash."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "consumer.c"
+    src.write_text("""
+#include <stdio.h>
+#include <string.h>
+#include "clipn.h"
+int main(void) {
+  clipn_gemm_desc d;
+  memset(&d, 0, sizeof d);            /* an empty problem: rejected by argument validation before any CUDA call */
+  int rc = clipn_gemm(&d, 0);
+  printf("version %d rc %d err %s\\n", clipn_version(), rc, clipn_last_error());
+  return 0;
+}
+""")
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-l:" + os.path.basename(L.LIB_PATH), "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.startswith("version 100 rc -"), out
+    assert "gemm" in out
+
+
 def test_product_path_refuses_cpu_tensors():
     import torch
     from open_clip_b200 import ops
