@@ -27,8 +27,9 @@ BF16, F32 = torch.bfloat16, torch.float32
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module: "NativeClipLoss", image_features, text_features, logit_scale, logit_bias):
-        if logit_bias is not None:
-            raise ClipnError("NativeClipLoss: logit_bias is a SigLIP parameter; use NativeSigLipLoss")
+        # loss.py:100-116 adds logit_bias to every logit; softmax cross-entropy is invariant to a constant added to a
+        # whole row, so the value is unchanged and d loss / d logit_bias = sum(softmax - onehot) = 0.
+        ctx.bias_like = logit_bias.detach() if logit_bias is not None else None
         if not image_features.is_cuda:
             raise ClipnError("NativeClipLoss runs on CUDA tensors only; there is no CPU fallback")
         B, E = image_features.shape
@@ -84,7 +85,8 @@ class _ClipLossFn(torch.autograd.Function):
         g = dloss.to(F32)
         d_img = (d_img * g.to(d_img.dtype)).to(ctx.in_dtypes[0])
         d_txt = (d_txt * g.to(d_txt.dtype)).to(ctx.in_dtypes[1])
-        return None, d_img, d_txt, (d_scale * g).to(ctx.in_dtypes[2]), None
+        d_bias = torch.zeros_like(ctx.bias_like) if ctx.bias_like is not None else None
+        return None, d_img, d_txt, (d_scale * g).to(ctx.in_dtypes[2]), d_bias
 
 
 class NativeClipLoss(nn.Module):

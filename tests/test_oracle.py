@@ -78,6 +78,23 @@ def test_other_baseline_geometries_match_reference_fixture(golden_dir, fixture, 
     assert abs(float(loss) - g["loss"]) <= 1e-5 * max(1.0, abs(g["loss"]))
 
 
+def test_clip_loss_is_invariant_to_logit_bias():
+    """ClipLoss with a logit_bias (loss.py:100-116 adds it to every logit): the value does not change and the bias
+    gets a zero gradient — the identity NativeClipLoss relies on when a model built with init_logit_bias is trained
+    with the softmax loss."""
+    g = torch.Generator().manual_seed(0)
+    img = torch.nn.functional.normalize(torch.randn(16, 32, generator=g), dim=-1).double().requires_grad_(True)
+    txt = torch.nn.functional.normalize(torch.randn(16, 32, generator=g), dim=-1).double().requires_grad_(True)
+    scale = torch.tensor(14.0, dtype=torch.float64)
+    bias = torch.tensor(-10.0, dtype=torch.float64, requires_grad=True)
+    with_bias = O.clip_loss(img, txt, scale, bias)
+    without = O.clip_loss(img, txt, scale)
+    assert abs(float(with_bias) - float(without)) < 1e-12
+    gi, gb = torch.autograd.grad(with_bias, (img, bias))
+    gi0, = torch.autograd.grad(without, (img,))
+    assert abs(float(gb)) < 1e-12 and (gi - gi0).abs().max() < 1e-12
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_multi_rank_losses_match_gloo_reference_fixture(golden_dir, world):
     gold = _load(golden_dir, f"loss_w{world}.pt")
