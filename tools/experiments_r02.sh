@@ -12,6 +12,10 @@ export PYTHONPATH=.
   echo "== attention timing: default, then prefetch"
   timeout 120 python tools/attn_bench.py 1024 50 12 0 1024 77 8 1
   CLIPN_ATTN_BWD_PREFETCH=1 timeout 120 python tools/attn_bench.py 1024 50 12 0 1024 77 8 1
+  echo "== towers on two streams: parity, then the step time against the default"
+  CLIPN_TOWER_STREAMS=1 timeout 200 python -m pytest tests/test_gpu_model.py -x -q -m gpu -k "tiny or train_steps" 2>&1 | tail -3
+  timeout 200 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e | cut -c1-220
+  CLIPN_TOWER_STREAMS=1 timeout 200 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-e2e | cut -c1-220
   echo "== GEMM shapes: default tile, then 128-wide tile"
   timeout 200 python tools/gemm_bench.py 1024
   CLIPN_GEMM_TILE_N=128 timeout 200 python tools/gemm_bench.py 1024
