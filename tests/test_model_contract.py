@@ -131,6 +131,52 @@ def test_accumulated_grads_never_alias_the_gradient_arena():
     assert m._unalias_grads("visual") == 0 and m._unalias_grads("text") == 0
 
 
+def test_tower_autograd_glue_accumulates_across_backward_calls(monkeypatch):
+    """The autograd node of a tower (one Function per tower, every parameter an input) with the kernel schedules
+    replaced by recorders: gradients come back with each parameter's dtype, a second backward without zero_grad adds
+    to the first (micro-batch accumulation), and zero_grad(set_to_none=True) starts over."""
+    from open_clip_b200 import ops, tower
+    from open_clip_b200.model import _TowerFn
+    c = CONFIGS["tiny"]
+    m = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], device="cpu")
+    calls = {"n": 0}
+
+    def fake_fwd(P, cfg, inp, normalize, ws, save, checkpoint=False):
+        return torch.zeros(inp.shape[0], cfg.embed_dim), (tower.TowerSaved(batch=inp.shape[0]) if save else None)
+
+    def fake_bwd(P, G, cfg, saved, dfeat, ws):
+        calls["n"] += 1
+        for g in G.values():
+            g.add_(float(calls["n"]))  # the kernels accumulate into the arena the node zeroed
+
+    monkeypatch.setattr(tower, "vision_forward", fake_fwd)
+    monkeypatch.setattr(tower, "vision_backward", fake_bwd)
+    monkeypatch.setattr(ops, "cast_f32_to_bf16", lambda x, out=None: out.copy_(x.to(BF16)))
+    params = dict(m.named_parameters())
+    plist = [params[n] for n in m._tower_param_names["visual"]]
+    image = torch.zeros(2, 3, 64, 64)
+
+    def run():
+        _TowerFn.apply(m, "visual", True, True, image, *plist).sum().backward()
+
+    run()
+    for p in plist:
+        assert p.grad is not None and p.grad.dtype == p.dtype and float(p.grad.float().mean()) == 1.0
+    run()  # no zero_grad in between: 1 + 2
+    assert all(float(p.grad.float().mean()) == 3.0 for p in plist)
+    for p in plist:
+        p.grad = None
+    run()
+    assert all(float(p.grad.float().mean()) == 3.0 for p in plist)
+    assert all(p.grad is None for n, p in params.items() if not n.startswith("visual."))
+    # a frozen parameter gets no gradient and does not disturb the others (lock_image_tower path)
+    m.lock_image_tower(unlocked_groups=1)
+    for p in plist:
+        p.grad = None
+    run()
+    assert params["visual.proj"].grad is not None and params["visual.conv1.weight"].grad is None
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="authoring container only")
 def test_reference_task_optimizer_and_train_step_drive_the_native_objects(monkeypatch):
     """The reference's OWN CLIPTask, create_optimizer and train-step closure (clip_task.py:28-46, optim.py:336,
