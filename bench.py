@@ -28,6 +28,8 @@ if ROOT not in sys.path:
 
 FWD_GFLOP_PER_PAIR = 14.78          # docs/model_profile.csv:8 (ViT-B-32), SURVEY §8d
 STEP_GFLOP_PER_PAIR = 3 * FWD_GFLOP_PER_PAIR
+# forward GFLOP per pair of the other BASELINE models (docs/model_profile.csv); step = 3x (no recompute)
+FWD_GFLOP_BY_MODEL = {"ViT-B-32": FWD_GFLOP_PER_PAIR, "ViT-B-16": 41.09, "ViT-L-14-336": 395.22}
 
 
 def load_peaks():
@@ -162,6 +164,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="local batch per GPU (BASELINE config: 4096)")
     ap.add_argument("--model", default="ViT-B-32")
+    ap.add_argument("--grad-checkpointing", action="store_true", help="BASELINE config 4 (ViT-L-14-336) runs with it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -208,6 +211,9 @@ def main():
     B = args.batch
     torch.manual_seed(0)
     model = create_model(args.model, output_dict=True, device=dev)
+    if args.grad_checkpointing:
+        model.set_grad_checkpointing(True)
+    step_gflop = 3 * FWD_GFLOP_BY_MODEL.get(args.model, FWD_GFLOP_PER_PAIR)
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
@@ -363,10 +369,10 @@ def main():
                                      "frac": fam_flops / (fam_ms * 1e-3) / 1e12 / peaks["bf16_sustained"] if fam_ms else None,
                                      "launches_timed": len(ops.PROFILE_EVENTS),
                                      "share_of_step": (fam_ms / args.steps) / ms_step},
-            "roofline_step": {"bound": "tensor", "achieved": pairs_per_s / world * STEP_GFLOP_PER_PAIR / 1e3,
+            "roofline_step": {"bound": "tensor", "achieved": pairs_per_s / world * step_gflop / 1e3,
                               "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                              "frac": pairs_per_s / world * STEP_GFLOP_PER_PAIR / 1e3 / peaks["bf16_sustained"],
-                              "flops_per_pair": STEP_GFLOP_PER_PAIR * 1e9},
+                              "frac": pairs_per_s / world * step_gflop / 1e3 / peaks["bf16_sustained"],
+                              "flops_per_pair": step_gflop * 1e9},
             "roofline_logits_gemm": logits_roofline,
             "gpu_launches": launches,
             "clocks": clocks,
