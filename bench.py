@@ -143,17 +143,82 @@ def logits_gemm_roofline(sig_time, sig_count, peak_tflops):
     if n == 0 or ms <= 0:
         return None
     tf = sum(2.0 * s[0] * s[1] * s[2] * sig_count[s] for s in lse_sigs) / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tc2_kernel<256,LSE> (peer-read logits GEMM + row LSE) + lse_combine",
+    return {"bound": "tensor", "kernel": "gemm_peer_kernel<128,LSE> (both directions in one launch: peer-read column "
+                                        "tiles stationary in smem + online row LSE) + lse_combine",
             "achieved": tf, "peak": peak_tflops, "unit": "TFLOP/s", "frac": tf / peak_tflops, "launches_timed": n,
             "avg_launch_ms": ms / n, "shape_mnk": [list(s[:3]) for s in lse_sigs]}
 
 
-def workload_config(model, batch, world):
-    """The `config` object of the JSON line — identical for the native and the reference arm."""
-    return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, local_loss"
-                        + (" + gather_with_grad fused into the logits GEMM" if world > 1 else " only"),
+def workload_config(model, batch, world, siglip=False, ckpt=False):
+    """The `config` object of the native arm's JSON line."""
+    if siglip:
+        loss = "SigLipLoss, peer text/image blocks read in place (no neighbour exchange)"
+    else:
+        loss = "ClipLoss local_loss" + (" + gather_with_grad, gather fused into the logits GEMM" if world > 1 else " only")
+    return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, {loss}"
+                        + (", grad-checkpointed blocks" if ckpt else ""),
             "global_batch": world * batch, "parallelism": f"dp{world}", "optimizer": "AdamW fused (torch)",
-            "cache": "inputs (1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"}
+            "cache": "inputs (>= 1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"}
+
+
+def reference_config(batch, cores, gpus):
+    """`config` of the reference arm: what the CPU leg really runs (the reference's CPU-runnable BASELINE config 0),
+    named next to the native workload it is the baseline for."""
+    return {"workload": f"ViT-B-32 fp32, batch {batch}, CPU {cores} threads (reference CLIPTask + train_step + AdamW, "
+                        f"oracle port); baseline for the native arm at {gpus}xB200",
+            "global_batch": batch, "parallelism": f"cpu{cores}", "optimizer": "AdamW (torch, CPU)"}
+
+
+def parity_block(model, loss_fn, image, text, rank, world, siglip):
+    """Oracle parity of the loss at the BENCHMARKED shape, outside the timed region: this step's features (bf16, from the
+    native towers) go through the native loss (value + feature / logit_scale gradients) and, gathered with NCCL,
+    through the oracle restatement of the reference's multi-rank semantics on rank 0 (fp32, on the GPU for speed —
+    the oracle is device-agnostic torch code).  Tolerances: loss 1e-2 abs, feature gradients 1.5e-2 rel-L2,
+    logit_scale gradient 2e-2 rel."""
+    import torch
+    import torch.distributed as dist
+    from oracle import clip_oracle as O
+    with torch.no_grad():
+        out = model(image=image, text=text)
+    fi = out["image_features"].detach().clone().requires_grad_(True)
+    ft = out["text_features"].detach().clone().requires_grad_(True)
+    sc = out["logit_scale"].detach().float().clone().requires_grad_(True)
+    if siglip:
+        lb = out["logit_bias"].detach().float().clone().requires_grad_(True)
+        loss = loss_fn(fi, ft, sc, lb)
+    else:
+        loss = loss_fn(fi, ft, sc)
+    loss.backward()
+    if world > 1:
+        all_i = [torch.empty_like(fi) for _ in range(world)]
+        all_t = [torch.empty_like(ft) for _ in range(world)]
+        dist.all_gather(all_i, fi.detach())
+        dist.all_gather(all_t, ft.detach())
+    else:
+        all_i, all_t = [fi.detach()], [ft.detach()]
+    res = None
+    if rank == 0:
+        ri, rt = [t.float() for t in all_i], [t.float() for t in all_t]
+        if siglip:
+            ref, d_img, d_txt, d_scale, d_bias = O.siglip_loss_rank_grads(ri, rt, sc.detach(), lb.detach(), 0)
+        else:
+            ref, d_img, d_txt, d_scale = O.clip_loss_rank_grads(ri, rt, sc.detach(), 0, True, True)
+
+        def rel(a, b):
+            return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+        res = {"loss": float(loss), "loss_ref": float(ref), "loss_abs_err": abs(float(loss) - float(ref)),
+               "dfeat_rel_l2": max(rel(fi.grad, d_img), rel(ft.grad, d_txt)),
+               "dscale_rel": abs(float(sc.grad) - float(d_scale)) / (abs(float(d_scale)) + 1e-30),
+               "shape": {"world": world, "local_batch": int(fi.shape[0]), "embed": int(fi.shape[1])},
+               "oracle": "oracle/clip_oracle.py %s (fp32 torch on cuda:0, rank 0)"
+                         % ("siglip_loss_rank_grads" if siglip else "clip_loss_rank_grads local_loss+gather_with_grad"),
+               "exchange": getattr(loss_fn, "exchange_mode", "local"),
+               "tol": {"loss_abs": 1e-2 if not siglip else 2e-2 * abs(float(ref)) + 1e-3, "dfeat_rel_l2": 1.5e-2 if not siglip else 2e-2,
+                       "dscale_rel": 2e-2}}
+        res["ok"] = bool(res["loss_abs_err"] <= res["tol"]["loss_abs"] and res["dfeat_rel_l2"] <= res["tol"]["dfeat_rel_l2"]
+                         and res["dscale_rel"] <= res["tol"]["dscale_rel"])
+    model.zero_grad(set_to_none=True)
+    return res
 
 
 def main():
@@ -165,6 +230,9 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="local batch per GPU (BASELINE config: 4096)")
     ap.add_argument("--model", default="ViT-B-32")
     ap.add_argument("--grad-checkpointing", action="store_true", help="BASELINE config 4 (ViT-L-14-336) runs with it")
+    ap.add_argument("--siglip", action="store_true",
+                    help="BASELINE config 5: SigLipLoss, init_logit_scale=ln 10, init_logit_bias=-10 (main.py:259-261)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity block (outside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -183,9 +251,8 @@ def main():
             "impl": "reference", "metric": "image-text pairs/sec (full train step)", "value": r["value"],
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            # same workload as the native arm (one full train step of the named model; pairs/s); each CPU step is the
-            # bounded sample described in cpu_baseline.sample (batch 32, fp32 — the reference's CPU-runnable config 0)
-            "config": workload_config(args.model, args.batch, max(1, args.gpus)),
+            # what really ran: the reference's CPU-runnable config 0 (ViT-B-32 fp32, batch 32) on the host threads
+            "config": reference_config(32, r["cores"], max(1, args.gpus)),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -194,9 +261,9 @@ def main():
     import torch
     import torch.distributed as dist
     from open_clip_b200 import _lib, ops
-    from open_clip_b200.loss import NativeClipLoss
+    from open_clip_b200.loss import NativeClipLoss, NativeSigLipLoss
     from open_clip_b200.model import create_model
-    from oracle import clip_oracle as O  # only for the cpu_baseline leg + synthetic data recipe
+    from oracle import clip_oracle as O  # checker only: cpu_baseline leg, parity block, synthetic data recipe
 
     _lib.lib()  # fail loudly if the CUDA library is missing
     torch.cuda.set_device(local_rank)
@@ -210,14 +277,18 @@ def main():
 
     B = args.batch
     torch.manual_seed(0)
-    model = create_model(args.model, output_dict=True, device=dev)
+    mkw = dict(init_logit_scale=math.log(10), init_logit_bias=-10.0) if args.siglip else {}
+    model = create_model(args.model, output_dict=True, device=dev, **mkw)
     if args.grad_checkpointing:
         model.set_grad_checkpointing(True)
     step_gflop = 3 * FWD_GFLOP_BY_MODEL.get(args.model, FWD_GFLOP_PER_PAIR)
     if world > 1:
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    loss_fn = NativeClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+    if args.siglip:
+        loss_fn = NativeSigLipLoss(rank=rank, world_size=world)
+    else:
+        loss_fn = NativeClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
     named = list(model.named_parameters())
     no_wd = model.no_weight_decay()
     decay = [p for n, p in named if p.ndim > 1 and n not in no_wd]
@@ -242,7 +313,10 @@ def main():
     def train_step(image, text):
         opt.zero_grad(set_to_none=True)
         out = module(image=image, text=text)
-        loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"])
+        if args.siglip:
+            loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"], out["logit_bias"])
+        else:
+            loss = loss_fn(out["image_features"], out["text_features"], out["logit_scale"])
         loss.backward()
         opt.step()
         with torch.no_grad():
@@ -331,6 +405,10 @@ def main():
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e}
 
+    parity = None
+    if not args.no_parity:
+        parity = parity_block(model, loss_fn, d_images[0], d_texts[0], rank, world, args.siglip)
+
     if rank == 0:
         epi_names = ["STORE", "BIAS_GELU", "BIAS_RESID", "DGELU", "ACCUM_F32(split-K wgrad)", "STORE_F32", "LSE",
                      "CLIP_DLOGITS", "SIGLIP", "BIAS_GELU_GRAD", "MUL_AUX"]
@@ -344,22 +422,29 @@ def main():
         gemm_ms = [0] * (sig_count[top] if top else 0)
         top_name = ("gemm_tc2_kernel<256,%s> M=%d N=%d K=%d%s" % (epi_names[top[3]], top[0], top[1], top[2],
                     " (MN-major operands)" if top[4] else "")) if top else "n/a"
-        # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r01_ncu_pair_gelu.txt,
-        # r01_ncu_pair_dgelu.txt: dram__bytes_read.sum + dram__bytes_write.sum at M = 51200), scaled linearly in M
-        ncu_traffic_m51200 = {(1, 3072, 768): 658.25e6, (9, 3072, 768): 658.25e6, (3, 3072, 768): 679.6e6}
-        traffic = None
-        if top and (top[3], top[1], top[2]) in ncu_traffic_m51200:
-            traffic = ncu_traffic_m51200[(top[3], top[1], top[2])] * top[0] / 51200.0
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of THIS kernel signature, taken from an
+        # `ncu --set full` capture of the current binary and recorded in profiles/ncu_traffic.json by
+        # tools/ncu_traffic.py ({"<epi>,<N>,<K>": {"m": M, "bytes": B, "source": "..."}}; scaled linearly in M).
+        # null when no capture of the timed signature exists — never a number from a different kernel.
+        traffic, traffic_src = None, None
+        try:
+            tbl = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tbl.get("%d,%d,%d" % (top[3], top[1], top[2])) if top else None
+            if ent:
+                traffic, traffic_src = ent["bytes"] * top[0] / ent["m"], ent.get("source")
+        except (OSError, ValueError, KeyError):
+            pass
         logits_roofline = logits_gemm_roofline(sig_time, sig_count, peaks["bf16_sustained"])
         out = {
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args.model, B, world),
+            "config": workload_config(args.model, B, world, args.siglip, args.grad_checkpointing),
             "roofline": {"bound": "tensor", "kernel": top_name,
                          "share_of_step": (sig_time[top] / args.steps) / ms_step if top else None,
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "algorithmic_bytes": (2.0 * (top[0] * top[2] + top[1] * top[2]) +
                                                2.0 * top[0] * top[1] * (2 if top[3] in (1, 9) else 1)) if top else None,
                          "launches_timed": len(gemm_ms), "avg_launch_ms": avg_ms,
@@ -382,9 +467,15 @@ def main():
             out["e2e"] = e2e
         if cpu_base is not None:
             out["cpu_baseline"] = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(out))
+        if parity is not None:
+            out["parity"] = parity
+        print(json.dumps(out), flush=True)
+    parity_failed = parity is not None and not parity["ok"]
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity_failed:
+        sys.stderr.write("bench.py: PARITY FAILED against the oracle: %s\n" % json.dumps(parity))
+        sys.exit(3)
 
 
 if __name__ == "__main__":

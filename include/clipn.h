@@ -178,31 +178,55 @@ int clipn_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int32_t n
 int clipn_cast_f32_to_bf16(const float* x, void* y, int64_t n, clipn_stream_t stream);
 
 /* ---- contrastive losses --------------------------------------------------------------------------
- * ClipLoss (loss.py:57-141), local_loss form: this rank's B rows against all N = W*B columns.
- * `feats_cols` lists W device pointers (peer-mapped for other ranks: the all-gather of
- * gather_features loss.py:29-54 is replaced by direct NVLink reads inside the GEMM's TMA loads), each
- * bf16 [B,E].  Computes row LSE + label logit for one direction:
- *   lse[m] = logsumexp_n( scale * rows[m] . cols[n] ),  pos[m] = scale * rows[m] . cols[label_offset+m]
- * workspace: fp32, at least clipn_clip_lse_workspace(B, N) elements. */
-int64_t clipn_clip_lse_workspace(int32_t b, int32_t n);
-int clipn_clip_lse_fwd(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                       float scale, const float* scale_dev, int32_t label_offset, float* lse, float* pos,
-                       float* workspace, clipn_stream_t stream);
-/* dlogits (bf16 [B,N]) for one direction, see CLIPN_EPI_CLIP_DLOGITS; col_lse is the OTHER direction's
- * global LSE vector [N] (all ranks), scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
-int clipn_clip_dlogits(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                       float scale, const float* scale_dev, int32_t label_offset, const float* row_lse,
-                       const float* col_lse, float col_w, float gscale, void* dlogits, float* scalar_acc,
-                       clipn_stream_t stream);
-/* d_rows ([B,E], fp32 if out_is_f32 else bf16) = alpha * dlogits[B,N] @ concat(feats_cols)[N,E] */
-int clipn_clip_dfeat(const void* dlogits, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                     float alpha, const float* alpha_dev, void* d_rows, int32_t out_is_f32, clipn_stream_t stream);
+ * ClipLoss (loss.py:57-141) in its local_loss form — this rank's B rows against all N = W*B columns, both
+ * directions (logits_per_image rows, logits_per_text rows; loss.py:102-104) — and SigLipLoss (loss.py:314-489).
+ *
+ * FUSED FORWARD.  `txt_cols` / `img_cols` list W device pointers, each bf16 [B,E]: rank r's feature buffer,
+ * peer-mapped into this process (CUDA IPC / symmetric memory) for r != rank.  ONE kernel launch streams every
+ * rank's buffer tile by tile through the tensor cores over NVLink — the two all-gathers of gather_features
+ * (loss.py:29-54) are fused into the logits GEMM (loss.py:102-110), every peer byte crosses NVLink once — and,
+ * when gather_txt / gather_img (bf16 [N,E], local) are given, leaves the gathered operands behind for the backward.
+ *   lse[0*B + m] = logsumexp_n( s * img[m] . txt_all[n] )      lse[1*B + m] = logsumexp_n( s * txt[m] . img_all[n] )
+ *   loss_acc[0] += ( sum_m lse_img[m] - pos_img[m]  +  sum_m lse_txt[m] - pos_txt[m] ) / (2B)      (loss.py:135-139)
+ * with s = scale * (*scale_dev) and pos = the label logit (column rank*B + m, loss.py:82-83).
+ * Shapes: E % 64 == 0, E <= 1024, W <= 8, and B % 128 == 0 (B % 64 for E > 512) when W > 1;
+ * clipn_peer_gemm_tile_n() returns 0 for shapes the fused kernel does not take (use the generic calls below on
+ * operands gathered by the caller).  workspace: fp32, clipn_clip_fwd_fused_workspace(W, B, E) elements. */
+int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e);
+int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e);
+int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
+                         const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e, float scale,
+                         const float* scale_dev, void* gather_txt, void* gather_img, float* lse, float* loss_acc,
+                         float* workspace, clipn_stream_t stream);
+/* SigLipLoss forward (+ d(logits) when dl_img / dl_txt are given), same operand convention.  Direction 0 (image rows
+ * x all text columns) accumulates the loss value (loss.py:351-367: every other rank's text block is a negative_only
+ * block, loss.py:410-487), d scale and d bias (scalar_acc[0], [1]) and writes dl_img = gscale * d loss / d logits
+ * (bf16 [B, ld]); direction 1 (text rows x all image columns) only writes dl_txt.  Because a SigLIP logit's gradient
+ * depends on nothing but the pair itself, rank r obtains d loss / d txt_r from ITS OWN text rows against the gathered
+ * image columns: the reverse neighbour exchange of the reference (loss.py:287-307) carries no data here. */
+int clipn_siglip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
+                           const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e,
+                           const float* scale_dev, const float* bias_dev, float gscale, void* gather_txt,
+                           void* gather_img, float* loss_acc, float* scalar_acc, void* dl_img, void* dl_txt, int64_t ld,
+                           clipn_stream_t stream);
 
-/* SigLipLoss block (loss.py:351-367): loss_acc[0] += sum softplus-form loss of one [B x B] block,
- * dlogits (bf16 [B,B], optional) = d loss/d logits * gscale, scalar_acc[0]/[1] += d scale / d bias. */
-int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, const float* scale_dev,
-                       const float* bias_dev, int32_t negative_only, float gscale, float* loss_acc, void* dlogits,
-                       float* scalar_acc, clipn_stream_t stream);
+/* GENERIC pieces (one local column operand `feats_cols` bf16 [n,E]; m local rows): the backward of both losses and
+ * the forward for shapes outside the fused kernel's envelope.
+ *   lse[m] = logsumexp_n( scale * rows[m] . cols[n] ),  pos[m] = scale * rows[m] . cols[label_offset+m]
+ * workspace: fp32, at least clipn_clip_lse_workspace(m, n) elements.  n % 8 == 0. */
+int64_t clipn_clip_lse_workspace(int32_t m, int32_t n);
+int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e, float scale,
+                       const float* scale_dev, int32_t label_offset, float* lse, float* pos, float* workspace,
+                       clipn_stream_t stream);
+/* dlogits (bf16 [m, ld]) for one direction, see CLIPN_EPI_CLIP_DLOGITS; col_lse is the OTHER direction's
+ * global LSE vector [n] (all ranks), scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
+int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e, float scale,
+                       const float* scale_dev, int32_t label_offset, const float* row_lse, const float* col_lse,
+                       float col_w, float gscale, void* dlogits, int64_t ld, float* scalar_acc, clipn_stream_t stream);
+/* d_rows (fp32 [m,E], zeroed by the caller) += alpha * dlogits[m,n] @ feats_cols[n,E]; split-K over n in `splits`
+ * chunks (TMA reduce-add) so that the [m x E] output fills the machine. */
+int clipn_clip_dfeat(const void* dlogits, int64_t ld, const void* feats_cols, int32_t m, int32_t n, int32_t e,
+                     float alpha, const float* alpha_dev, float* d_rows, int32_t splits, clipn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -65,12 +65,16 @@ SIGNATURES = {
     "clipn_l2norm_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _I64, _I32, _P]),
     "clipn_colsum": (C.c_int, [_P, _I64, _P, _I64, _I32, _P]),
     "clipn_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "clipn_peer_gemm_tile_n": (_I32, [_I32, _I32, _I32]),
+    "clipn_clip_fwd_fused_workspace": (C.c_int64, [_I32, _I32, _I32]),
+    "clipn_clip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32, _F,
+                                       _P, _P, _P, _P, _P, _P, _P]),
+    "clipn_siglip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32,
+                                         _P, _P, _F, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "clipn_clip_lse_workspace": (C.c_int64, [_I32, _I32]),
-    "clipn_clip_lse_fwd": (C.c_int, [_P, C.POINTER(C.c_void_p), _I32, _I32, _I32, _F, _P, _I32, _P, _P, _P, _P]),
-    "clipn_clip_dlogits": (C.c_int, [_P, C.POINTER(C.c_void_p), _I32, _I32, _I32, _F, _P, _I32, _P, _P, _F, _F, _P, _P,
-                                     _P]),
-    "clipn_clip_dfeat": (C.c_int, [_P, C.POINTER(C.c_void_p), _I32, _I32, _I32, _F, _P, _P, _I32, _P]),
-    "clipn_siglip_block": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _I32, _F, _P, _P, _P, _P]),
+    "clipn_clip_lse_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I32, _P, _P, _P, _P]),
+    "clipn_clip_dlogits": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I32, _P, _P, _F, _F, _P, _I64, _P, _P]),
+    "clipn_clip_dfeat": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _F, _P, _P, _I32, _P]),
 }
 
 _lib = None

@@ -1,50 +1,88 @@
 """Peer-memory feature exchange over NVLink 5 / NVSwitch.
 
 Replaces the two NCCL all-gathers of `gather_features` (reference loss.py:29-54): every rank writes its
-[B,E] bf16 image/text features into a symmetric (peer-mapped) buffer once; the logits GEMM then reads every
-peer's buffer directly through per-rank TMA tensor maps (libclipn `feats_cols`), so the gather is fused
-into the GEMM's operand loads.  The backward's [N,E] gradient reduce-scatter is eliminated by exchanging
-only the two row-LSE vectors (2*N fp32), see loss.py in this package.
+[B,E] bf16 image/text features into a symmetric (peer-mapped) buffer once; the fused logits kernel then reads
+every peer's buffer directly through per-rank TMA tensor maps (libclipn `txt_cols` / `img_cols`), so the gather is
+fused into the GEMM's operand loads, each peer tile crossing NVLink once, and leaves a local gathered copy behind
+as a by-product.  The backward reads only that local copy; the [N,E] gradient reduce-scatter of
+`_all_gather_with_grad` (loss.py:23-26) is eliminated by exchanging only the two row-LSE vectors (2*N fp32) for
+ClipLoss and nothing at all for SigLipLoss (see loss.py in this package).
+
+Envelope of the fused path: one NVLink domain with `torch.distributed._symmetric_memory`, world <= 8, per-rank batch a
+multiple of 128 (64 for embed dims above 512), embed dim a multiple of 64 and <= 1024.  Anything else — more ranks,
+several nodes, ragged batches — takes the NCCL fallback: `all_gather_into_tensor` into the same local gathered
+buffers, followed by the generic single-map kernels.  Same values, same gradient conventions.
 
 torch.distributed supplies the bootstrap (rendezvous + symmetric-memory handles), as in the reference
-(open_clip_train/distributed.py:102-166); no NCCL collective touches the feature matrices.
+(open_clip_train/distributed.py:102-166).
 """
 from __future__ import annotations
 
-from typing import List, Optional
+import os
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
+from . import ops
 
-class PeerFeatureExchange:
-    """Symmetric [2, B, E] bf16 buffer (slot 0 image, slot 1 text) mapped into every rank."""
+BF16 = torch.bfloat16
+
+
+class FeatureGather:
+    """Per-(batch, embed) exchange state of one loss module.
+
+    peer mode : symmetric [2 slots, 2 (image, text), B, E] bf16 buffer mapped into every rank.  Steps alternate
+                between the two slots, so ONE barrier per step is enough: the barrier of step t (data of step t
+                visible everywhere) also proves that every rank finished reading step t-1's slot — which is the
+                slot step t+1 overwrites.
+    nccl mode : no symmetric memory; `gather_nccl` all-gathers into the local buffers.
+    Both modes own `all_img` / `all_txt`: local bf16 [W*B, E] copies of every rank's features for the backward.
+    """
 
     def __init__(self, batch: int, embed: int, device: torch.device, group: Optional[dist.ProcessGroup] = None):
-        import torch.distributed._symmetric_memory as symm_mem
-
         self.group = group if group is not None else dist.group.WORLD
         self.rank = dist.get_rank(self.group)
         self.world = dist.get_world_size(self.group)
         self.batch, self.embed = batch, embed
-        self.buf = symm_mem.empty((2, batch, embed), dtype=torch.bfloat16, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, self.group)
-        slot = batch * embed * 2
-        self.img_ptrs: List[int] = [int(p) for p in self.hdl.buffer_ptrs]
-        self.txt_ptrs: List[int] = [int(p) + slot for p in self.hdl.buffer_ptrs]
+        self.all_img = torch.empty((self.world * batch, embed), dtype=BF16, device=device)
+        self.all_txt = torch.empty((self.world * batch, embed), dtype=BF16, device=device)
+        self.step = 0
+        self.mode = "nccl"
+        self.why_nccl = ""
+        if os.environ.get("CLIPN_FORCE_NCCL_GATHER") == "1":
+            self.why_nccl = "CLIPN_FORCE_NCCL_GATHER=1"
+        elif ops.peer_gemm_tile_n(self.world, batch, embed) == 0:
+            self.why_nccl = (f"shape outside the fused kernel's envelope (world {self.world}, batch {batch}, "
+                             f"embed {embed})")
+        else:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.buf = symm_mem.empty((2, 2, batch, embed), dtype=BF16, device=device)
+                self.hdl = symm_mem.rendezvous(self.buf, self.group)
+                ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                slot, half = 2 * batch * embed * 2, batch * embed * 2
+                self._img_ptrs = [[p + s * slot for p in ptrs] for s in range(2)]
+                self._txt_ptrs = [[p + s * slot + half for p in ptrs] for s in range(2)]
+                self.mode = "peer"
+            except Exception as exc:  # no symmetric memory on this transport (multi-node, no P2P, old torch)
+                self.why_nccl = f"symmetric memory unavailable: {type(exc).__name__}: {exc}"
 
-    def publish(self, image_features: torch.Tensor, text_features: torch.Tensor):
-        """barrier (peers finished reading last step's data) -> write -> barrier (data visible to peers)."""
+    def publish(self, image_features: torch.Tensor, text_features: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor,
+                                                                                           List[int], List[int]]:
+        """peer mode: write this step's features into the current slot, barrier; returns (local image view, local text
+        view, per-rank image pointers, per-rank text pointers)."""
+        s = self.step & 1
+        self.step += 1
+        self.buf[s, 0].copy_(image_features)
+        self.buf[s, 1].copy_(text_features)
         self.hdl.barrier(channel=0)
-        self.buf[0].copy_(image_features)
-        self.buf[1].copy_(text_features)
-        self.hdl.barrier(channel=1)
+        return self.buf[s, 0], self.buf[s, 1], self._img_ptrs[s], self._txt_ptrs[s]
 
-    def local_image(self) -> torch.Tensor:
-        return self.buf[0]
-
-    def local_text(self) -> torch.Tensor:
-        return self.buf[1]
+    def gather_nccl(self, image_features: torch.Tensor, text_features: torch.Tensor):
+        """Fallback: the reference's two all-gathers (loss.py:43-46), into the local gathered buffers."""
+        dist.all_gather_into_tensor(self.all_img, image_features.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(self.all_txt, text_features.contiguous(), group=self.group)
 
 
 def all_gather_vectors(vecs: torch.Tensor, group=None) -> torch.Tensor:

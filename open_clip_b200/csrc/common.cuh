@@ -303,6 +303,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // 8 FFMA + 5 FMUL + 2 MUFU + 1 LOP per element for gelu AND its derivative (raw MUFU ops: the range-checked
 // exp2f()/__fdividef() wrappers cost 3 FSETP/FSEL + 3 FMUL more per element, and the GELU epilogues are issue-bound).
 __device__ __forceinline__ void gelu_core(float x, float& half_one_plus_erf, float& gauss) {

@@ -18,6 +18,7 @@
 // loss.py:102-110 and the autograd dgrad/wgrad of each.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "gemm_internal.cuh"
@@ -226,59 +227,108 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= p.alpha;  // reduce-added to C by the caller (TMA in the tensor-core path)
   } else if constexpr (EPI == CLIPN_EPI_LSE) {
-    const int label = row + p.label_offset;
+    // online log-sum-exp in the log2 domain: t = (alpha*acc + bias) * log2(e); one FFMA + FMNMX + FADD + MUFU.EX2 +
+    // FADD per element (raw ex2.approx: the range-checked exp2f() costs ~6 more issue slots per element and this
+    // epilogue competes with a K = 512 mainloop).  run_max / pos are kept in the log2 domain until epi_finish.
+    const float a2 = p.alpha * kLog2e, b2 = p.logit_bias * kLog2e;
     float cmax = -INFINITY;
+    if (nvalid == 32) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      v[i] = (i < nvalid) ? v[i] * p.alpha + p.logit_bias : -INFINITY;
-      cmax = fmaxf(cmax, v[i]);
-      if (col + i == label) {
-        st.pos = v[i];
-        st.has_pos = true;
+      for (int i = 0; i < 32; ++i) {
+        v[i] = fmaf(v[i], a2, b2);
+        cmax = fmaxf(cmax, v[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        v[i] = (i < nvalid) ? fmaf(v[i], a2, b2) : -INFINITY;
+        cmax = fmaxf(cmax, v[i]);
       }
     }
-    const float nmax = fmaxf(st.run_max, cmax);
-    float s = 0.f;
+    // the label column of this warp's 32 rows lies in [row0 + off, row0 + off + 32): test the chunk once per warp
+    const int lab0 = row - static_cast<int>(lane_id()) + p.label_offset;
+    if (col < lab0 + 32 && col + 32 > lab0) {
+      const int label = row + p.label_offset;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) s += exp2f((v[i] - nmax) * kLog2e);
-    st.run_sum = st.run_sum * exp2f((st.run_max - nmax) * kLog2e) + s;
+      for (int i = 0; i < 32; ++i)
+        if (col + i == label) {
+          st.pos = v[i];
+          st.has_pos = true;
+        }
+    }
+    const float nmax = fmaxf(st.run_max, cmax);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      s0 += ex2_approx(v[i] - nmax);
+      s1 += ex2_approx(v[i + 1] - nmax);
+    }
+    st.run_sum = st.run_sum * ex2_approx(st.run_max - nmax) + (s0 + s1);
     st.run_max = nmax;
   } else if constexpr (EPI == CLIPN_EPI_CLIP_DLOGITS) {
     const int label = row + p.label_offset;
-    const float rl = row_ok ? __ldg(p.row_lse + row) : 0.f;
+    const float a2 = p.alpha * kLog2e, b2 = p.logit_bias * kLog2e;
+    const float rl2 = row_ok ? __ldg(p.row_lse + row) * kLog2e : 0.f;
+    const int lab0 = row - static_cast<int>(lane_id()) + p.label_offset;
+    const bool has_label = col < lab0 + 32 && col + 32 > lab0;  // warp-uniform
+    float cl2[32];
+    if (p.col_w != 0.f) {
+      // column LSE vector: 32 consecutive floats, the same for every lane (broadcast loads through L1)
+      const float4* src = reinterpret_cast<const float4*>(p.col_lse + col);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float dot = v[i];
-      const float s = dot * p.alpha + p.logit_bias;
-      const float pr = exp2f((s - rl) * kLog2e);
-      const float pc =
-          (p.col_w != 0.f && i < nvalid) ? p.col_w * exp2f((s - __ldg(p.col_lse + col + i)) * kLog2e) : 0.f;
-      const float onehot = (col + i == label) ? 1.f : 0.f;
-      v[i] = p.gscale * (pr + pc - (1.f + p.col_w) * onehot);
-      if (row_ok && i < nvalid) {
-        st.acc0 += (pr - onehot) * dot;
-        st.acc1 += (pr - onehot);
+      for (int i = 0; i < 8; ++i) {
+        const float4 t = (i * 4 < nvalid) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        cl2[4 * i] = t.x * kLog2e; cl2[4 * i + 1] = t.y * kLog2e; cl2[4 * i + 2] = t.z * kLog2e; cl2[4 * i + 3] = t.w * kLog2e;
       }
     }
-  } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
+    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       const float dot = v[i];
-      const float z = dot * p.alpha + p.logit_bias;
-      const float y = (!p.negative_only && (col + i == row + p.label_offset)) ? 1.f : -1.f;
-      const float yz = y * z;
-      // -logsigmoid(yz) = softplus(-yz) = max(-yz,0) + log1p(exp(-|yz|))
-      const float e = __expf(-fabsf(yz));
-      const float loss = fmaxf(-yz, 0.f) + log1pf(e);
-      // d/dz = -y * sigmoid(-yz)
-      const float sig = (yz >= 0.f) ? e / (1.f + e) : 1.f / (1.f + e);
-      const float dz = -y * sig;
-      v[i] = p.gscale * dz;
-      if (row_ok && i < nvalid) {
-        st.run_sum += loss;
-        st.acc0 += dz * dot;
-        st.acc1 += dz;
+      const float s2 = fmaf(dot, a2, b2);
+      float pr = ex2_approx(s2 - rl2);
+      float pc = (p.col_w != 0.f) ? p.col_w * ex2_approx(s2 - cl2[i]) : 0.f;
+      if (i >= nvalid) { pr = 0.f; pc = 0.f; }
+      float g = pr + pc;
+      if (has_label && col + i == label) {
+        g -= 1.f + p.col_w;
+        pr -= 1.f;
       }
+      v[i] = p.gscale * g;
+      a0 = fmaf(pr, dot, a0);
+      a1 += pr;
+    }
+    if (row_ok) {
+      st.acc0 += a0;
+      st.acc1 += a1;
+    }
+  } else if constexpr (EPI == CLIPN_EPI_SIGLIP) {
+    // -logsigmoid(yz) = max(-yz, 0) + log1p(e), e = exp(-|yz|); d/dz = -y * sigmoid(-yz).  Raw MUFU ops
+    // (ex2 / rcp / lg2 .approx): 3 per element with the loss value, 2 without (p.part_sum == nullptr).
+    const int lab0 = row - static_cast<int>(lane_id()) + p.label_offset;
+    const bool has_label = !p.negative_only && col < lab0 + 32 && col + 32 > lab0;  // warp-uniform
+    const int label = row + p.label_offset;
+    const bool want_loss = p.part_sum != nullptr;
+    float ls = 0.f, a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float dot = v[i];
+      const float z = fmaf(dot, p.alpha, p.logit_bias);
+      const float y = (has_label && col + i == label) ? 1.f : -1.f;
+      const float yz = y * z;
+      const float e = ex2_approx(-fabsf(yz) * kLog2e);
+      const float r = rcp_approx(1.f + e);                 // 1 / (1 + e)
+      const float sig = (yz >= 0.f) ? e * r : r;            // sigmoid(-yz)
+      const float dz = (i < nvalid) ? -y * sig : 0.f;
+      v[i] = p.gscale * dz;
+      a0 = fmaf(dz, dot, a0);
+      a1 += dz;
+      if (want_loss && i < nvalid) ls += fmaxf(-yz, 0.f) - lg2_approx(r) * 0.69314718055994531f;  // log1p(e) = -ln r
+    }
+    if (row_ok) {
+      st.run_sum += ls;
+      st.acc0 += a0;
+      st.acc1 += a1;
     }
   }
 }
@@ -288,9 +338,10 @@ template <int EPI>
 __device__ __forceinline__ void epi_finish(const GemmParams& p, int row, int slab, EpiState& st) {
   if constexpr (EPI == CLIPN_EPI_LSE) {
     if (row < p.m) {
-      p.part_max[static_cast<int64_t>(slab) * p.m + row] = st.run_max;
+      constexpr float kLn2 = 0.69314718055994531f;
+      p.part_max[static_cast<int64_t>(slab) * p.m + row] = st.run_max * kLn2;  // log2 domain -> natural
       p.part_sum[static_cast<int64_t>(slab) * p.m + row] = st.run_sum;
-      if (st.has_pos) p.pos[row] = st.pos;
+      if (st.has_pos) p.pos[row] = st.pos * kLn2;
     }
   } else if constexpr (EPI == CLIPN_EPI_CLIP_DLOGITS) {
     const float a0 = warp_sum(st.acc0), a1 = warp_sum(st.acc1);
@@ -558,6 +609,7 @@ __device__ __forceinline__ void stage64_read32(uint8_t* buf, int r, float (&v)[3
 }
 
 #include "gemm_pair.cuh"
+#include "gemm_peer.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // CUDA-core restatement (tests only): identical slab structure and epilogue math, no tensor cores, plain
@@ -682,6 +734,99 @@ static int launch_ref(const GemmParams& p, const RefOperands& ops, int bn, cudaS
   gemm_ref_kernel<EPI><<<grid, 128, 0, stream>>>(p, ops, bn);
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
+}
+
+int peer_gemm_tile_n(int world, int rows_per_map, int e) {
+  if (e <= 0 || e % BK != 0 || e > 1024 || world < 1 || world > kMaxBMaps || rows_per_map <= 0) return 0;
+  const int bn = e <= 512 ? 128 : 64;
+  if (world > 1 && rows_per_map % bn != 0) return 0;  // a column tile must not straddle two ranks' buffers
+  return bn;
+}
+
+template <int BN, int EPI>
+static int launch_peer(const PeerTmaps& tm, const PeerParams& p, cudaStream_t stream) {
+  using Cfg = PeerCfg<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(gemm_peer_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int64_t total = static_cast<int64_t>(p.dirs) * p.tiles_n * p.tiles_m;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = total < max_clusters ? static_cast<int>(total) : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CLIPN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_peer_kernel<BN, EPI>, tm, p));
+  return CLIPN_OK;
+}
+
+int peer_gemm_launch(const PeerGemmDesc& d, cudaStream_t stream) {
+  CLIPN_REQUIRE(d.dirs == 1 || d.dirs == 2, "peer gemm: 1 or 2 directions");
+  CLIPN_REQUIRE(d.epilogue == CLIPN_EPI_LSE || d.epilogue == CLIPN_EPI_SIGLIP, "peer gemm: LSE or SIGLIP epilogue");
+  CLIPN_REQUIRE(d.m > 0, "peer gemm: empty problem");
+  const int bn = peer_gemm_tile_n(d.world, d.rows_per_map, d.e);
+  CLIPN_REQUIRE(bn != 0,
+                "peer gemm: needs embed dim % 64 == 0 and <= 1024, world <= 8, per-rank rows % 128 == 0 when world > 1");
+  int cc_major = 0, sms = 0, cc_minor = 0;
+  clipn_device_info(&sms, &cc_major, &cc_minor);
+  CLIPN_REQUIRE(cc_major == 10, "peer gemm: the tcgen05 kernels require an sm_100 (B200) device");
+  const int n = d.world * d.rows_per_map;
+  PeerParams p;
+  memset(&p, 0, sizeof(p));
+  p.m = d.m; p.n = n; p.kblocks = d.e / BK;
+  p.rank = d.world > 1 ? d.rank : 0;
+  p.rows_per_map = d.rows_per_map;
+  p.tiles_m = (d.m + 2 * BM - 1) / (2 * BM);
+  p.tiles_n = (n + bn - 1) / bn;
+  p.dirs = d.dirs;
+  p.label_offset = d.label_offset; p.negative_only = d.negative_only;
+  p.alpha = d.alpha; p.alpha_dev = d.alpha_dev; p.logit_bias = d.logit_bias; p.logit_bias_dev = d.logit_bias_dev;
+  p.gscale = d.gscale;
+  p.gather = 0;
+  PeerTmaps tm;
+  int rc;
+  for (int dir = 0; dir < d.dirs; ++dir) {
+    CLIPN_REQUIRE(d.rows[dir] != nullptr && d.cols[dir] != nullptr, "peer gemm: null operand");
+    if (d.epilogue == CLIPN_EPI_LSE)
+      CLIPN_REQUIRE(d.part_max[dir] && d.part_sum[dir] && d.pos[dir], "peer gemm: LSE buffers required");
+    p.part_max[dir] = d.part_max[dir]; p.part_sum[dir] = d.part_sum[dir]; p.pos[dir] = d.pos[dir];
+    p.c[dir] = d.c[dir]; p.scalar_acc[dir] = d.scalar_acc[dir];
+    rc = make_tmap_2d(&tm.a[dir], d.rows[dir], 2, d.e, d.m, static_cast<uint64_t>(d.e) * 2, BK, BM, 128);
+    if (rc) return rc;
+    for (int i = 0; i < d.world; ++i) {
+      CLIPN_REQUIRE(d.cols[dir][i] != nullptr, "peer gemm: null column pointer");
+      rc = make_tmap_2d(&tm.b[dir][i], d.cols[dir][i], 2, d.e, d.rows_per_map, static_cast<uint64_t>(d.e) * 2, BK, bn / 2,
+                        128);
+      if (rc) return rc;
+    }
+    if (d.gather[dir] != nullptr) {
+      p.gather = 1;
+      rc = make_tmap_2d(&tm.g[dir], d.gather[dir], 2, d.e, n, static_cast<uint64_t>(d.e) * 2, BK, bn / 2, 128);
+      if (rc) return rc;
+    }
+    if (d.epilogue == CLIPN_EPI_SIGLIP && d.c[dir] != nullptr) {
+      CLIPN_REQUIRE(d.ldc % 8 == 0 && d.ldc >= n, "peer gemm: ldc must be a multiple of 8 and >= n");
+      rc = make_tmap_2d(&tm.c[dir], d.c[dir], 2, n, d.m, static_cast<uint64_t>(d.ldc) * 2, 64, 32, 128);
+      if (rc) return rc;
+    }
+  }
+  if (p.gather)
+    for (int dir = 0; dir < d.dirs; ++dir)
+      CLIPN_REQUIRE(d.gather[dir] != nullptr, "peer gemm: gather buffers must be given for every direction or none");
+  if (d.epilogue == CLIPN_EPI_LSE)
+    return bn == 128 ? launch_peer<128, CLIPN_EPI_LSE>(tm, p, stream) : launch_peer<64, CLIPN_EPI_LSE>(tm, p, stream);
+  return bn == 128 ? launch_peer<128, CLIPN_EPI_SIGLIP>(tm, p, stream) : launch_peer<64, CLIPN_EPI_SIGLIP>(tm, p, stream);
 }
 
 #define CLIPN_DISPATCH_EPI(EPIVAR, MACRO)                                   \

@@ -1,36 +1,63 @@
-// Contrastive-loss entry points (ClipLoss loss.py:57-141, SigLipLoss loss.py:314-489) on top of the tcgen05
-// GEMM: the logits are never materialised in the forward (online log-sum-exp in the GEMM epilogue), and the
-// column operand is read tile-by-tile straight from every rank's (peer-mapped) feature buffer through one TMA
-// tensor map per rank — the all-gather of gather_features (loss.py:29-54) is fused into the GEMM.
+// Contrastive-loss entry points (ClipLoss loss.py:57-141, SigLipLoss loss.py:314-489) on top of the tcgen05 GEMMs.
+//
+// Forward (fused, clipn_clip_fwd_fused / clipn_siglip_fwd_fused): ONE launch of the peer-streaming kernel
+// (gemm_peer.cuh) computes both directions' logits against every rank's features, read tile by tile straight from
+// the owning rank's peer-mapped buffer (the all-gather of gather_features loss.py:29-54 is fused into the GEMM; the
+// logits are never materialised: online log-sum-exp / softplus in the epilogue) and leaves a local copy of the
+// gathered operands behind.  Backward: d(logits) tiles are recomputed from the LSE vectors against the LOCAL
+// gathered copy (generic kernel, one tensor map), written once in bf16 and contracted by a split-K GEMM.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "gemm_internal.cuh"
 
 namespace clipn {
 
-// combine per-slab (max, sum) partials into the row LSE: lse[m] = log sum_n exp(s[m,n])
+// combine per-slab (max, sum) partials into the row LSE: lse[m] = log sum_n exp(s[m,n]); optionally accumulate
+// loss_acc += loss_scale * sum_m (lse[m] - pos[m])   (the cross-entropy value of this direction)
 __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ part_max,
-                                                          const float* __restrict__ part_sum, float* __restrict__ lse,
-                                                          int m, int slabs) {
+                                                          const float* __restrict__ part_sum,
+                                                          const float* __restrict__ pos, float* __restrict__ lse,
+                                                          float* __restrict__ loss_acc, float loss_scale, int m,
+                                                          int slabs, int64_t dir_stride_part, int64_t dir_stride_vec) {
+  const int dir = blockIdx.y;
+  part_max += dir * dir_stride_part;
+  part_sum += dir * dir_stride_part;
+  lse += dir * dir_stride_vec;
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= m) return;
-  float mx = -INFINITY;
-  for (int s = 0; s < slabs; ++s) mx = fmaxf(mx, part_max[static_cast<int64_t>(s) * m + row]);
-  float sum = 0.f;
-  for (int s = 0; s < slabs; ++s) {
-    const float pm = part_max[static_cast<int64_t>(s) * m + row];
-    if (pm != -INFINITY) sum += part_sum[static_cast<int64_t>(s) * m + row] * __expf(pm - mx);
+  float local = 0.f;
+  if (row < m) {
+    float mx = -INFINITY;
+    for (int s = 0; s < slabs; ++s) mx = fmaxf(mx, part_max[static_cast<int64_t>(s) * m + row]);
+    float sum = 0.f;
+    for (int s = 0; s < slabs; ++s) {
+      const float pm = part_max[static_cast<int64_t>(s) * m + row];
+      if (pm != -INFINITY) sum += part_sum[static_cast<int64_t>(s) * m + row] * __expf(pm - mx);
+    }
+    const float l = mx + __logf(sum);
+    lse[row] = l;
+    if (pos != nullptr) local = l - pos[dir * dir_stride_vec + row];
   }
-  lse[row] = mx + __logf(sum);
+  if (loss_acc != nullptr) {
+    __shared__ float red[8];
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += red[i];
+      atomicAdd(loss_acc, t * loss_scale);
+    }
+  }
 }
 
-static void base_desc(clipn_gemm_desc& d, const void* rows, int b, int n, int e, float scale,
+static void base_desc(clipn_gemm_desc& d, const void* rows, const void* cols, int m, int n, int e, float scale,
                       const float* scale_dev) {
   memset(&d, 0, sizeof(d));
   d.a = rows; d.lda = e; d.a_mn_major = 0;
-  d.ldb = e; d.b_mn_major = 0;
-  d.m = b; d.n = n; d.k = e;
+  d.b = cols; d.ldb = e; d.b_mn_major = 0;
+  d.m = m; d.n = n; d.k = e;
   d.alpha = scale; d.alpha_dev = scale_dev; d.splits = 1;
 }
 
@@ -38,84 +65,136 @@ static void base_desc(clipn_gemm_desc& d, const void* rows, int b, int n, int e,
 
 using namespace clipn;
 
-extern "C" int64_t clipn_clip_lse_workspace(int32_t b, int32_t n) {
-  const int bn = gemm_tile_n(n);
-  const int64_t slabs = 2 * static_cast<int64_t>((n + bn - 1) / bn);
-  return 2 * slabs * b;
+// ---------------------------------------------------------------------------------------------------
+// fused forward (peer-streaming kernel)
+// ---------------------------------------------------------------------------------------------------
+extern "C" int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e) { return peer_gemm_tile_n(world, b, e); }
+
+extern "C" int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e) {
+  const int bn = peer_gemm_tile_n(world, b, e);
+  if (bn == 0) return 0;
+  const int64_t n = static_cast<int64_t>(world) * b;
+  const int64_t slabs = (n + bn - 1) / bn;
+  return 2 * (2 * slabs * b + b);  // per direction: part_max + part_sum [slabs, b], pos [b]
 }
 
-extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b,
-                                  int32_t e, float scale, const float* scale_dev, int32_t label_offset, float* lse,
-                                  float* pos, float* workspace, clipn_stream_t stream) {
-  CLIPN_REQUIRE(feats_rows && feats_cols && lse && pos && workspace, "clip_lse_fwd: null pointer");
-  CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_lse_fwd: world must be 1..8");
-  const int n = world * b;
-  const int bn = gemm_tile_n(n);
-  const int slabs = 2 * ((n + bn - 1) / bn);
-  clipn_gemm_desc d;
-  base_desc(d, feats_rows, b, n, e, scale, scale_dev);
-  d.b = feats_cols[0];
+extern "C" int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
+                                    const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e,
+                                    float scale, const float* scale_dev, void* gather_txt, void* gather_img, float* lse,
+                                    float* loss_acc, float* workspace, clipn_stream_t stream) {
+  CLIPN_REQUIRE(img_rows && txt_rows && txt_cols && img_cols && lse && workspace, "clip_fwd_fused: null pointer");
+  const int bn = peer_gemm_tile_n(world, b, e);
+  CLIPN_REQUIRE(bn != 0, "clip_fwd_fused: unsupported shape (see clipn_peer_gemm_tile_n)");
+  CLIPN_REQUIRE((gather_txt == nullptr) == (gather_img == nullptr), "clip_fwd_fused: both gather buffers or none");
+  const int64_t n = static_cast<int64_t>(world) * b;
+  const int slabs = static_cast<int>((n + bn - 1) / bn);
+  const int64_t part = static_cast<int64_t>(slabs) * b;
+  float* pos = workspace + 4 * part;  // [2, b]
+  PeerGemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.rows[0] = img_rows; d.cols[0] = txt_cols; d.gather[0] = gather_txt;
+  d.rows[1] = txt_rows; d.cols[1] = img_cols; d.gather[1] = gather_img;
+  d.dirs = 2; d.world = world; d.rank = rank; d.m = b; d.rows_per_map = b; d.e = e;
   d.epilogue = CLIPN_EPI_LSE;
-  d.part_max = workspace;
-  d.part_sum = workspace + static_cast<int64_t>(slabs) * b;
-  d.pos = pos;
-  d.label_offset = label_offset;
-  int rc = gemm_launch(d, feats_cols, world, b, false, static_cast<cudaStream_t>(stream));
+  d.alpha = scale; d.alpha_dev = scale_dev;
+  d.label_offset = world > 1 ? rank * b : 0;
+  for (int dir = 0; dir < 2; ++dir) {
+    d.part_max[dir] = workspace + dir * part;
+    d.part_sum[dir] = workspace + 2 * part + dir * part;
+    d.pos[dir] = pos + dir * static_cast<int64_t>(b);
+  }
+  int rc = peer_gemm_launch(d, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
-  lse_combine_kernel<<<(b + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(d.part_max, d.part_sum, lse, b, slabs);
+  dim3 grid((b + 255) / 256, 2);
+  lse_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, workspace + 2 * part, pos, lse,
+                                                                         loss_acc, 1.0f / (2.0f * b), b, slabs, part, b);
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }
 
-extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* const* feats_cols, int32_t world, int32_t b,
-                                  int32_t e, float scale, const float* scale_dev, int32_t label_offset,
-                                  const float* row_lse, const float* col_lse, float col_w, float gscale, void* dlogits, float* scalar_acc,
-                                  clipn_stream_t stream) {
-  CLIPN_REQUIRE(feats_rows && feats_cols && row_lse && dlogits, "clip_dlogits: null pointer");
-  CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_dlogits: world must be 1..8");
-  const int n = world * b;
+extern "C" int clipn_siglip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
+                                      const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e,
+                                      const float* scale_dev, const float* bias_dev, float gscale, void* gather_txt,
+                                      void* gather_img, float* loss_acc, float* scalar_acc, void* dl_img, void* dl_txt,
+                                      int64_t ld, clipn_stream_t stream) {
+  CLIPN_REQUIRE(img_rows && txt_rows && txt_cols && img_cols && loss_acc && scale_dev, "siglip_fwd_fused: null pointer");
+  CLIPN_REQUIRE((dl_img == nullptr) == (dl_txt == nullptr), "siglip_fwd_fused: both d(logits) buffers or none");
+  const int dirs = dl_txt != nullptr ? 2 : 1;  // the text direction only produces gradients
+  PeerGemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.rows[0] = img_rows; d.cols[0] = txt_cols; d.gather[0] = gather_txt;
+  d.rows[1] = txt_rows; d.cols[1] = img_cols; d.gather[1] = dirs == 2 ? gather_img : nullptr;
+  if (dirs == 1) d.gather[0] = nullptr;        // nothing downstream reads the gathered copy without a backward
+  d.dirs = dirs; d.world = world; d.rank = rank; d.m = b; d.rows_per_map = b; d.e = e;
+  d.epilogue = CLIPN_EPI_SIGLIP;
+  d.alpha = 1.0f; d.alpha_dev = scale_dev; d.logit_bias = 0.f; d.logit_bias_dev = bias_dev;
+  d.gscale = gscale;
+  d.label_offset = world > 1 ? rank * b : 0;
+  d.part_sum[0] = loss_acc; d.scalar_acc[0] = scalar_acc;  // value, d scale, d bias: image direction only
+  d.c[0] = dl_img; d.c[1] = dl_txt; d.ldc = ld;
+  return peer_gemm_launch(d, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// generic (single tensor map, local operands) pieces: forward fallback for shapes the peer kernel does not take,
+// and the backward
+// ---------------------------------------------------------------------------------------------------
+extern "C" int64_t clipn_clip_lse_workspace(int32_t m, int32_t n) {
+  const int bn = gemm_tile_n(n);
+  const int64_t slabs = 2 * static_cast<int64_t>((n + bn - 1) / bn);
+  return 2 * slabs * m;
+}
+
+extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e,
+                                  float scale, const float* scale_dev, int32_t label_offset, float* lse, float* pos,
+                                  float* workspace, clipn_stream_t stream) {
+  CLIPN_REQUIRE(feats_rows && feats_cols && lse && pos && workspace, "clip_lse_fwd: null pointer");
+  const int bn = gemm_tile_n(n);
+  const int slabs = 2 * ((n + bn - 1) / bn);
   clipn_gemm_desc d;
-  base_desc(d, feats_rows, b, n, e, scale, scale_dev);
-  d.b = feats_cols[0];
+  base_desc(d, feats_rows, feats_cols, m, n, e, scale, scale_dev);
+  d.epilogue = CLIPN_EPI_LSE;
+  d.part_max = workspace;
+  d.part_sum = workspace + static_cast<int64_t>(slabs) * m;
+  d.pos = pos;
+  d.label_offset = label_offset;
+  const void* bp[1] = {feats_cols};
+  int rc = gemm_launch(d, bp, 1, 0, false, static_cast<cudaStream_t>(stream));
+  if (rc) return rc;
+  lse_combine_kernel<<<dim3((m + 255) / 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d.part_max, d.part_sum, nullptr, lse, nullptr, 0.f, m, slabs, 0, 0);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e,
+                                  float scale, const float* scale_dev, int32_t label_offset, const float* row_lse,
+                                  const float* col_lse, float col_w, float gscale, void* dlogits, int64_t ld,
+                                  float* scalar_acc, clipn_stream_t stream) {
+  CLIPN_REQUIRE(feats_rows && feats_cols && row_lse && dlogits, "clip_dlogits: null pointer");
+  clipn_gemm_desc d;
+  base_desc(d, feats_rows, feats_cols, m, n, e, scale, scale_dev);
   d.epilogue = CLIPN_EPI_CLIP_DLOGITS;
-  d.c = dlogits; d.ldc = n;
+  d.c = dlogits; d.ldc = ld;
   d.row_lse = row_lse; d.col_lse = col_lse; d.col_w = col_w; d.gscale = gscale;
   d.scalar_acc = scalar_acc;
   d.label_offset = label_offset;
-  return gemm_launch(d, feats_cols, world, b, false, static_cast<cudaStream_t>(stream));
+  const void* bp[1] = {feats_cols};
+  return gemm_launch(d, bp, 1, 0, false, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int clipn_clip_dfeat(const void* dlogits, const void* const* feats_cols, int32_t world, int32_t b, int32_t e,
-                                float alpha, const float* alpha_dev, void* d_rows, int32_t out_is_f32,
+extern "C" int clipn_clip_dfeat(const void* dlogits, int64_t ld, const void* feats_cols, int32_t m, int32_t n, int32_t e,
+                                float alpha, const float* alpha_dev, float* d_rows, int32_t splits,
                                 clipn_stream_t stream) {
   CLIPN_REQUIRE(dlogits && feats_cols && d_rows, "clip_dfeat: null pointer");
-  CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_dfeat: world must be 1..8");
-  const int n = world * b;
   clipn_gemm_desc d;
   memset(&d, 0, sizeof(d));
-  d.a = dlogits; d.lda = n; d.a_mn_major = 0;       // [B, N], reduction over N
-  d.b = feats_cols[0]; d.ldb = e; d.b_mn_major = 1;  // each rank: [B(K rows), E] -> MN-major
+  d.a = dlogits; d.lda = ld; d.a_mn_major = 0;     // [m, n], reduction over n
+  d.b = feats_cols; d.ldb = e; d.b_mn_major = 1;  // [n (K rows), e] -> MN-major
   d.c = d_rows; d.ldc = e;
-  d.m = b; d.n = e; d.k = n;
-  d.alpha = alpha; d.alpha_dev = alpha_dev; d.splits = 1;
-  d.epilogue = out_is_f32 ? CLIPN_EPI_STORE_F32 : CLIPN_EPI_STORE;
-  return gemm_launch(d, feats_cols, world, b, false, static_cast<cudaStream_t>(stream));
-}
-
-extern "C" int clipn_siglip_block(const void* img, const void* txt, int32_t b, int32_t e, const float* scale_dev,
-                                  const float* bias_dev, int32_t negative_only, float gscale, float* loss_acc,
-                                  void* dlogits, float* scalar_acc, clipn_stream_t stream) {
-  CLIPN_REQUIRE(img && txt && loss_acc && scale_dev, "siglip_block: null pointer");
-  clipn_gemm_desc d;
-  base_desc(d, img, b, b, e, 1.0f, scale_dev);
-  d.b = txt;
-  d.epilogue = CLIPN_EPI_SIGLIP;
-  d.c = dlogits; d.ldc = b;
-  d.logit_bias = 0.f; d.logit_bias_dev = bias_dev;
-  d.negative_only = negative_only;
-  d.gscale = gscale;
-  d.part_sum = loss_acc;
-  d.scalar_acc = scalar_acc;
-  const void* bp[1] = {txt};
+  d.m = m; d.n = e; d.k = n;
+  d.alpha = alpha; d.alpha_dev = alpha_dev; d.splits = splits < 1 ? 1 : splits;
+  d.epilogue = CLIPN_EPI_ACCUM_F32;               // d_rows (fp32, caller-zeroed) += alpha * dlogits @ cols
+  const void* bp[1] = {feats_cols};
   return gemm_launch(d, bp, 1, 0, false, static_cast<cudaStream_t>(stream));
 }

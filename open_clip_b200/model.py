@@ -112,24 +112,27 @@ class _TowerFn(torch.autograd.Function):
             raise ClipnError("backward through a NativeCLIP tower that ran without saved activations")
         cfg = model._vcfg if which == "visual" else model._tcfg
         arena = model._grad_arena(which)
-        model._unalias_grads(which)
         arena["flat32"].zero_()
         G = arena["views32"]
         bwd = tower.vision_backward if which == "visual" else tower.text_backward
         bwd(P, G, cfg, ctx.saved, dfeat, model._scratch[which])
         ctx.saved = None
-        # bf16 params get bf16 grads (one cast over the contiguous low-precision segment)
+        # The fp32 arena is this node's ACCUMULATOR only; what autograd receives are views of two buffers owned by
+        # this call: one bf16 cast of the low-precision segment, one copy of the fp32 segment (2 launches, no
+        # per-parameter copies).  The arena can therefore be zeroed and refilled by the next backward of this tower —
+        # another micro-batch (`--accum-freq`, train.py:236-311), or a second use of the tower in the SAME graph
+        # (multi-view / multi-caption losses) whose first gradients still sit in the engine's input buffers.
         n_lowp = arena["n_lowp"]
-        if n_lowp:
-            ops.cast_f32_to_bf16(arena["flat32"][:n_lowp], out=arena["flat16"])
+        out16 = ops.cast_f32_to_bf16(arena["flat32"][:n_lowp], out=torch.empty_like(arena["flat16"])) if n_lowp else None
+        out32 = arena["flat32"][n_lowp:].clone()
         grads = []
         for n, p in zip(names, ctx.P.values()):
             if not p.requires_grad:
                 grads.append(None)
-            elif p.dtype == BF16:
-                grads.append(arena["views16"][n])
-            else:
-                grads.append(arena["views32"][n])
+                continue
+            off, k = arena["offsets"][n]
+            src = out16[off:off + k] if p.dtype == BF16 else out32[off - n_lowp:off - n_lowp + k]
+            grads.append(src.view(p.shape))
         return (None, None, None, None, None, *grads)
 
 
@@ -149,6 +152,14 @@ class NativeCLIP(nn.Module):
         self.context_length = t.get("context_length", 77)
         self.vocab_size = t.get("vocab_size", 49408)
         vw, tw = v["width"], t["width"]
+        if isinstance(v["image_size"], (tuple, list)):  # CLIPVisionCfg.image_size may be an (h, w) pair (model.py:41)
+            if len(set(v["image_size"])) != 1:
+                raise ClipnError(f"NativeCLIP supports square images only, got image_size={v['image_size']}")
+            v["image_size"] = int(v["image_size"][0])
+        if isinstance(v["patch_size"], (tuple, list)):
+            if len(set(v["patch_size"])) != 1:
+                raise ClipnError(f"NativeCLIP supports square patches only, got patch_size={v['patch_size']}")
+            v["patch_size"] = int(v["patch_size"][0])
         grid = v["image_size"] // v["patch_size"]
         mlp_ratio = v.get("mlp_ratio", 4.0)
         self._vcfg = tower.TowerCfg(width=vw, layers=v["layers"], heads=vw // 64, seq=grid * grid + 1, causal=False,
@@ -235,30 +246,8 @@ class NativeCLIP(nn.Module):
         self._arenas: Dict[str, dict] = {}
         self.grad_checkpointing = False
 
-    @torch.no_grad()
-    def _unalias_grads(self, which: str) -> int:
-        """Gradient accumulation (`--accum-freq`, train.py:236-311; or zero_grad(set_to_none=False)): autograd may keep
-        the arena views this tower returned as the parameters' `.grad` without copying them. Before the arena is
-        zeroed and refilled for the next micro-batch, give every such parameter its own copy, so the earlier
-        micro-batches' sum survives and autograd's `grad += new` adds two different buffers. Returns the number of
-        gradients that were detached (0 on the ordinary zero_grad(set_to_none=True) path)."""
-        a = self._arenas.get(which)
-        if a is None:
-            return 0
-        params = dict(self.named_parameters())
-        n_detached = 0
-        for n in self._tower_param_names[which]:
-            p = params[n]
-            if p.grad is None:
-                continue
-            view = a["views16"].get(n) if p.dtype == BF16 else a["views32"].get(n)
-            if view is not None and p.grad.data_ptr() == view.data_ptr():
-                p.grad = p.grad.clone()
-                n_detached += 1
-        return n_detached
-
     def _grad_arena(self, which: str) -> dict:
-        """Flat fp32 gradient accumulators for one tower (low-precision params first) + a bf16 shadow."""
+        """Flat fp32 gradient accumulators for one tower (low-precision params first)."""
         a = self._arenas.get(which)
         params = dict(self.named_parameters())
         names = self._tower_param_names[which]
@@ -271,14 +260,14 @@ class NativeCLIP(nn.Module):
             total = n_lowp + sum(pad(params[n].numel()) for n in highp)
             flat32 = torch.zeros(total, dtype=F32, device=dev)
             flat16 = torch.empty(n_lowp, dtype=BF16, device=dev)
-            v32, v16, off = {}, {}, 0
+            v32, offsets, off = {}, {}, 0
             for n in lowp + highp:
                 k = params[n].numel()
                 v32[n] = flat32[off:off + k].view(params[n].shape)
-                if n in lowp:
-                    v16[n] = flat16[off:off + k].view(params[n].shape)
+                offsets[n] = (off, k)
                 off += pad(k)
-            a = {"flat32": flat32, "flat16": flat16, "views32": v32, "views16": v16, "n_lowp": n_lowp}
+            # flat16 is only the shape/dtype template of the per-call bf16 gradient buffer (never written)
+            a = {"flat32": flat32, "flat16": flat16, "views32": v32, "offsets": offsets, "n_lowp": n_lowp}
             self._arenas[which] = a
         return a
 

@@ -270,53 +270,124 @@ def _ptr_array(ptrs: Sequence[int]):
     return arr
 
 
-def clip_lse_fwd(rows: torch.Tensor, col_ptrs: Sequence[int], scale: torch.Tensor, label_offset: int):
-    """Row log-sum-exp and label logit of scale * rows @ concat(cols).T; cols given as per-rank device pointers.
-    `scale` is a 1-element fp32 DEVICE tensor (no host sync)."""
-    _chk(rows, BF16, "lse.rows"); _chk(scale, F32, "lse.scale")
-    b, e = rows.shape
-    world = len(col_ptrs)
-    ws = torch.empty(L.lib().clipn_clip_lse_workspace(b, world * b), dtype=F32, device=rows.device)
-    lse = torch.empty(b, dtype=F32, device=rows.device)
-    pos = torch.zeros(b, dtype=F32, device=rows.device)
-    prof = PROFILE_KEY == "all"
-    if prof:  # bench.py: the fused gather + logits + LSE GEMM (and its tiny combine kernel) as one timed signature
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    _call(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
-                                       label_offset, lse.data_ptr(), pos.data_ptr(), ws.data_ptr(), _stream()))
-    if prof:
-        e1.record()
-        PROFILE_EVENTS.append((e0, e1, (b, world * b, e, L.EPI_LSE, False, False)))
+def peer_gemm_tile_n(world: int, b: int, e: int) -> int:
+    """Column-tile width of the fused peer-streaming forward for this shape, 0 if it does not take it."""
+    return int(L.lib().clipn_peer_gemm_tile_n(world, b, e))
+
+
+def _profiled(sig):
+    """bench.py instrumentation: CUDA events on the launching stream around one C-ABI call (context manager)."""
+    class _Ctx:
+        def __enter__(self):
+            self.on = PROFILE_KEY == "all"
+            if self.on:
+                self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                self.e0.record()
+
+        def __exit__(self, *exc):
+            if self.on and exc[0] is None:
+                self.e1.record()
+                PROFILE_EVENTS.append((self.e0, self.e1, sig))
+    return _Ctx()
+
+
+def clip_fwd_fused(img: torch.Tensor, txt: torch.Tensor, txt_ptrs: Sequence[int], img_ptrs: Sequence[int], rank: int,
+                   scale: torch.Tensor, gather_txt: Optional[torch.Tensor], gather_img: Optional[torch.Tensor]):
+    """Both directions of the ClipLoss forward in one launch (+ a tiny combine kernel): returns lse [2, B] (image rows,
+    text rows) and the 1-element loss accumulator (already the local cross-entropy value, loss.py:135-139).
+    `*_ptrs`: one device pointer per rank to that rank's bf16 [B, E] features (peer-mapped).  `gather_*`: optional
+    local bf16 [W*B, E] buffers that receive the gathered column operands as a by-product."""
+    _chk(img, BF16, "fused.img"); _chk(txt, BF16, "fused.txt"); _chk(scale, F32, "fused.scale")
+    b, e = img.shape
+    world = len(txt_ptrs)
+    ws = torch.empty(L.lib().clipn_clip_fwd_fused_workspace(world, b, e), dtype=F32, device=img.device)
+    lse = torch.empty((2, b), dtype=F32, device=img.device)
+    loss = torch.zeros(1, dtype=F32, device=img.device)
+    # bench.py: the fused gather + logits + LSE GEMM of BOTH directions (and its combine kernel) as one timed signature
+    with _profiled((2 * b, world * b, e, L.EPI_LSE, False, False)):
+        _call(L.lib().clipn_clip_fwd_fused(img.data_ptr(), txt.data_ptr(), _ptr_array(txt_ptrs), _ptr_array(img_ptrs),
+                                             world, rank, b, e, 1.0, scale.data_ptr(), _ptr(gather_txt),
+                                             _ptr(gather_img), lse.data_ptr(), loss.data_ptr(), ws.data_ptr(),
+                                             _stream()), 2)
+    return lse, loss
+
+
+def siglip_fwd_fused(img, txt, txt_ptrs, img_ptrs, rank, scale, bias, gscale, gather_txt, gather_img, loss_acc,
+                     scalar_acc, want_grad: bool):
+    """SigLipLoss forward in one launch; with want_grad also d(logits) of both directions (bf16 [B, ld])."""
+    _chk(img, BF16, "siglip.img"); _chk(txt, BF16, "siglip.txt")
+    b, e = img.shape
+    world = len(txt_ptrs)
+    n = world * b
+    ld = (n + 7) // 8 * 8
+    dl_i = torch.empty((b, ld), dtype=BF16, device=img.device) if want_grad else None
+    dl_t = torch.empty((b, ld), dtype=BF16, device=img.device) if want_grad else None
+    with _profiled(((2 if want_grad else 1) * b, n, e, L.EPI_SIGLIP, False, False)):
+        _call(L.lib().clipn_siglip_fwd_fused(img.data_ptr(), txt.data_ptr(), _ptr_array(txt_ptrs), _ptr_array(img_ptrs),
+                                               world, rank, b, e, scale.data_ptr(), bias.data_ptr(), gscale,
+                                               _ptr(gather_txt) if want_grad else None,
+                                               _ptr(gather_img) if want_grad else None, loss_acc.data_ptr(),
+                                               _ptr(scalar_acc), _ptr(dl_i), _ptr(dl_t), ld, _stream()))
+    return dl_i, dl_t
+
+
+def clip_lse_fwd(rows: torch.Tensor, cols: torch.Tensor, scale: torch.Tensor, label_offset: int):
+    """Generic (any E % 8 == 0, n % 8 == 0) row log-sum-exp and label logit of scale * rows @ cols.T; cols is one
+    LOCAL [n, E] tensor.  `scale` is a 1-element fp32 DEVICE tensor (no host sync)."""
+    _chk(rows, BF16, "lse.rows"); _chk(cols, BF16, "lse.cols"); _chk(scale, F32, "lse.scale")
+    m, e = rows.shape
+    n = cols.shape[0]
+    ws = torch.empty(L.lib().clipn_clip_lse_workspace(m, n), dtype=F32, device=rows.device)
+    lse = torch.empty(m, dtype=F32, device=rows.device)
+    pos = torch.zeros(m, dtype=F32, device=rows.device)
+    with _profiled((m, n, e, L.EPI_LSE, False, False)):
+        _call(L.lib().clipn_clip_lse_fwd(rows.data_ptr(), cols.data_ptr(), m, n, e, 1.0, scale.data_ptr(), label_offset,
+                                           lse.data_ptr(), pos.data_ptr(), ws.data_ptr(), _stream()), 2)
     return lse, pos
 
 
-def clip_dlogits(rows, col_ptrs, scale, label_offset, row_lse, col_lse, col_w, gscale, scalar_acc):
-    _chk(rows, BF16, "dlogits.rows")
-    b, e = rows.shape
-    world = len(col_ptrs)
-    out = torch.empty((b, world * b), dtype=BF16, device=rows.device)
-    _call(L.lib().clipn_clip_dlogits(rows.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, scale.data_ptr(),
-                                       label_offset, row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(),
-                                       _ptr(scalar_acc), _stream()))
+def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscale, scalar_acc):
+    _chk(rows, BF16, "dlogits.rows"); _chk(cols, BF16, "dlogits.cols")
+    m, e = rows.shape
+    n = cols.shape[0]
+    out = torch.empty((m, n), dtype=BF16, device=rows.device)
+    with _profiled((m, n, e, L.EPI_CLIP_DLOGITS, False, False)):
+        _call(L.lib().clipn_clip_dlogits(rows.data_ptr(), cols.data_ptr(), m, n, e, 1.0, scale.data_ptr(), label_offset,
+                                           row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(), n,
+                                           _ptr(scalar_acc), _stream()))
     return out
 
 
-def clip_dfeat(dlogits, col_ptrs, e, alpha: torch.Tensor, out_dtype=BF16):
-    _chk(dlogits, BF16, "dfeat.dlogits")
-    b = dlogits.shape[0]
-    world = len(col_ptrs)
-    out = torch.empty((b, e), dtype=out_dtype, device=dlogits.device)
-    _call(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), _ptr_array(col_ptrs), world, b, e, 1.0, alpha.data_ptr(),
-                                     out.data_ptr(), int(out_dtype == F32), _stream()))
+def clip_dfeat(dlogits, cols, alpha: torch.Tensor, n: Optional[int] = None):
+    """fp32 [m, E] = alpha * dlogits[:, :n] @ cols  (split-K over n, TMA reduce-add into a zeroed buffer)."""
+    _chk(dlogits, BF16, "dfeat.dlogits"); _chk(cols, BF16, "dfeat.cols")
+    m, ld = dlogits.shape
+    n = cols.shape[0] if n is None else n
+    e = cols.shape[1]
+    out = torch.zeros((m, e), dtype=F32, device=dlogits.device)
+    splits = wgrad_splits(m, e, n)
+    with _profiled((m, e, n, L.EPI_ACCUM_F32, False, True)):
+        _call(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), ld, cols.data_ptr(), m, n, e, 1.0, alpha.data_ptr(),
+                                         out.data_ptr(), splits, _stream()))
     return out
 
 
-def siglip_block(img, txt, scale, bias, negative_only, gscale, loss_acc, scalar_acc, want_grad: bool):
-    _chk(img, BF16, "siglip.img"); _chk(txt, BF16, "siglip.txt")
-    b, e = img.shape
-    dl = torch.empty((b, b), dtype=BF16, device=img.device) if want_grad else None
-    _call(L.lib().clipn_siglip_block(img.data_ptr(), txt.data_ptr(), b, e, scale.data_ptr(), bias.data_ptr(),
-                                       int(negative_only), gscale, loss_acc.data_ptr(), _ptr(dl), _ptr(scalar_acc),
-                                       _stream()))
+def siglip_dir(rows, cols, scale, bias, label_offset, gscale, loss_acc, scalar_acc, want_grad: bool):
+    """Generic SigLIP direction on a LOCAL column operand (fallback for shapes outside the fused kernel's envelope):
+    loss_acc / scalar_acc (optional) accumulate the value and d scale, d bias; returns d(logits) bf16 [m, n] or None."""
+    m, e = rows.shape
+    n = cols.shape[0]
+    dl = torch.empty((m, n), dtype=BF16, device=rows.device) if want_grad else None
+    d = L.GemmDesc()
+    d.a, d.lda, d.a_mn_major = rows.data_ptr(), e, 0
+    d.b, d.ldb, d.b_mn_major = cols.data_ptr(), e, 0
+    if dl is not None:
+        d.c, d.ldc = dl.data_ptr(), n
+    d.m, d.n, d.k = m, n, e
+    d.epilogue, d.alpha, d.splits = L.EPI_SIGLIP, 1.0, 1
+    d.alpha_dev, d.logit_bias_dev = scale.data_ptr(), bias.data_ptr()
+    d.gscale, d.label_offset, d.negative_only = gscale, label_offset, 0
+    d.part_sum = _ptr(loss_acc)
+    d.scalar_acc = _ptr(scalar_acc)
+    _call(L.lib().clipn_gemm(C.byref(d), _stream()))
     return dl

@@ -138,8 +138,9 @@ def block_forward(P: Dict[str, torch.Tensor], pre: str, cfg: TowerCfg, x: torch.
     # ln_2 -> c_fc + GELU -> c_proj + residual (transformer.py:295-299,329)
     h2 = torch.empty((M, d), dtype=BF16, device=dev) if keep else ws.get("h", (M, d), BF16, dev)
     _, m2, r2 = ops.layernorm_fwd(x_mid, P[pre + ".ln_2.weight"], P[pre + ".ln_2.bias"], out=h2, save_stats=save)
-    h_pre = torch.empty((M, 4 * d), dtype=BF16, device=dev) if save else ws.get("h_pre", (M, 4 * d), BF16, dev)
-    g = torch.empty((M, 4 * d), dtype=BF16, device=dev) if keep else ws.get("g", (M, 4 * d), BF16, dev)
+    hid = P[pre + ".mlp.c_fc.weight"].shape[0]  # int(d * mlp_ratio), model.py sizes c_fc / c_proj with it
+    h_pre = torch.empty((M, hid), dtype=BF16, device=dev) if save else ws.get("h_pre", (M, hid), BF16, dev)
+    g = torch.empty((M, hid), dtype=BF16, device=dev) if keep else ws.get("g", (M, hid), BF16, dev)
     # fast mode keeps gelu'(h) in the `h_pre` slot (and gelu(h)), so the backward epilogue is a plain multiply;
     # lean mode keeps the pre-activation h and re-derives both in the backward (CLIPN_EPI_DGELU)
     ops.gemm(h2, P[pre + ".mlp.c_fc.weight"], bias=P[pre + ".mlp.c_fc.bias"],
@@ -164,7 +165,8 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     M, d = dx_out.shape
     dev = dx_out.device
     # ---- MLP
-    dh = ws.get("dh", (M, 4 * d), BF16, dev)
+    hid = P[pre + ".mlp.c_fc.weight"].shape[0]
+    dh = ws.get("dh", (M, hid), BF16, dev)
     # dgrad of c_proj fused with GELU backward; re-materialises g = gelu(h_pre) unless the forward kept it
     # (the c_fc bias gradient = column sums of dh is accumulated by the same epilogue)
     if s.g is not None:
@@ -172,7 +174,7 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
         ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_MUL_AUX, aux=s.h_pre, out=dh,
                  col_sum=G[pre + ".mlp.c_fc.bias"])  # s.h_pre holds gelu'(h) in fast mode
     else:
-        g = ws.get("g", (M, 4 * d), BF16, dev)
+        g = ws.get("g", (M, hid), BF16, dev)
         ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g,
                  col_sum=G[pre + ".mlp.c_fc.bias"])
     _wgrad(dx_out, g, G[pre + ".mlp.c_proj.weight"])

@@ -309,7 +309,30 @@ def clip_loss(image_features: torch.Tensor, text_features: torch.Tensor, logit_s
     if logit_bias is not None:
         lpi = lpi + logit_bias
         lpt = lpt + logit_bias
-    labels = torch.arange(lpi.shape[0])
+    labels = torch.arange(lpi.shape[0], device=lpi.device)
+    return (F.cross_entropy(lpi, labels) + F.cross_entropy(lpt, labels)) / 2
+
+
+def _clip_loss_one_rank(r: int, image_features, text_features, logit_scale, local_loss: bool,
+                        gather_with_grad: bool) -> torch.Tensor:
+    """ClipLoss value on rank r of world_size = len(image_features) (loss.py:29-54,91-141)."""
+    if gather_with_grad:
+        imgs, txts = list(image_features), list(text_features)
+    else:
+        imgs = [f.detach() for f in image_features]
+        txts = [f.detach() for f in text_features]
+        if not local_loss:  # loss.py:47-50 splice the grad-carrying local tensors back in
+            imgs[r], txts[r] = image_features[r], text_features[r]
+    all_i, all_t = torch.cat(imgs), torch.cat(txts)
+    if local_loss:  # loss.py:102-104
+        lpi = logit_scale * image_features[r] @ all_t.T
+        lpt = logit_scale * text_features[r] @ all_i.T
+        B = lpi.shape[0]
+        labels = torch.arange(B, device=lpi.device) + B * r  # loss.py:82-83
+    else:  # loss.py:106-107
+        lpi = logit_scale * all_i @ all_t.T
+        lpt = lpi.T
+        labels = torch.arange(lpi.shape[0], device=lpi.device)
     return (F.cross_entropy(lpi, labels) + F.cross_entropy(lpt, labels)) / 2
 
 
@@ -318,28 +341,36 @@ def clip_loss_ranks(image_features: Sequence[torch.Tensor], text_features: Seque
     """Per-rank ClipLoss values for world_size = len(image_features) (loss.py:29-54,91-141).
     Gradient convention: with gather_with_grad the gathered tensors carry grad
     to every rank's features; without it only the local slice does (others are detached)."""
+    return [_clip_loss_one_rank(r, image_features, text_features, logit_scale, local_loss, gather_with_grad)
+            for r in range(len(image_features))]
+
+
+def clip_loss_rank_grads(image_features: Sequence[torch.Tensor], text_features: Sequence[torch.Tensor],
+                         logit_scale: torch.Tensor, rank: int, local_loss: bool, gather_with_grad: bool):
+    """What ONE rank of the reference sees after loss.backward(): (loss_rank, d image_features[rank],
+    d text_features[rank], d logit_scale).  Feature gradients are those of the SUM of every rank's loss (each rank
+    back-propagates its own loss and the gather's autograd routes the pieces to their owners, loss.py:23-26,47-50);
+    the logit_scale gradient is that of this rank's loss only.  Same numbers as differentiating
+    sum(clip_loss_ranks(...)), but one rank's graph at a time (memory-lean: benchmark-sized batches), on whatever
+    device the inputs live."""
     W = len(image_features)
-    out = []
+    img = [f.detach() for f in image_features]
+    txt = [f.detach() for f in text_features]
+    img[rank] = img[rank].clone().requires_grad_(True)
+    txt[rank] = txt[rank].clone().requires_grad_(True)
+    d_scale = None
+    value = None
     for r in range(W):
-        if gather_with_grad:
-            imgs, txts = list(image_features), list(text_features)
-        else:
-            imgs = [f.detach() for f in image_features]
-            txts = [f.detach() for f in text_features]
-            if not local_loss:  # loss.py:47-50 splice the grad-carrying local tensors back in
-                imgs[r], txts[r] = image_features[r], text_features[r]
-        all_i, all_t = torch.cat(imgs), torch.cat(txts)
-        if local_loss:  # loss.py:102-104
-            lpi = logit_scale * image_features[r] @ all_t.T
-            lpt = logit_scale * text_features[r] @ all_i.T
-            B = lpi.shape[0]
-            labels = torch.arange(B) + B * r  # loss.py:82-83
-        else:  # loss.py:106-107
-            lpi = logit_scale * all_i @ all_t.T
-            lpt = lpi.T
-            labels = torch.arange(lpi.shape[0])
-        out.append((F.cross_entropy(lpi, labels) + F.cross_entropy(lpt, labels)) / 2)
-    return out
+        scale = logit_scale.detach().clone().requires_grad_(True)
+        loss = _clip_loss_one_rank(r, img, txt, scale, local_loss, gather_with_grad)
+        if not loss.requires_grad:
+            continue
+        loss.backward()
+        if r == rank:
+            value, d_scale = loss.detach(), scale.grad.detach()
+    if value is None:
+        value = _clip_loss_one_rank(rank, img, txt, logit_scale.detach(), local_loss, gather_with_grad).detach()
+    return value, img[rank].grad, txt[rank].grad, d_scale
 
 
 def siglip_block_loss(image_features, text_features, logit_scale, logit_bias, negative_only=False):
@@ -348,10 +379,18 @@ def siglip_block_loss(image_features, text_features, logit_scale, logit_bias, ne
     if logit_bias is not None:
         logits = logits + logit_bias
     n = image_features.shape[0]
-    labels = -torch.ones((n, n), dtype=image_features.dtype)
+    labels = -torch.ones((n, n), dtype=image_features.dtype, device=image_features.device)
     if not negative_only:
-        labels = 2 * torch.eye(n, dtype=image_features.dtype) + labels
+        labels = 2 * torch.eye(n, dtype=image_features.dtype, device=image_features.device) + labels
     return -F.logsigmoid(labels * logits).sum() / n
+
+
+def _siglip_loss_one_rank(r: int, image_features, text_features, logit_scale, logit_bias) -> torch.Tensor:
+    loss = siglip_block_loss(image_features[r], text_features[r], logit_scale, logit_bias)
+    for s in range(len(image_features)):
+        if s != r:
+            loss = loss + siglip_block_loss(image_features[r], text_features[s], logit_scale, logit_bias, True)
+    return loss
 
 
 def siglip_loss_ranks(image_features: Sequence[torch.Tensor], text_features: Sequence[torch.Tensor],
@@ -359,15 +398,28 @@ def siglip_loss_ranks(image_features: Sequence[torch.Tensor], text_features: Seq
     """Per-rank SigLipLoss values (loss.py:406-489).  Every dist_impl visits each other rank's
     text block exactly once as a negative_only block, so the value is impl-independent
     (SURVEY §8c probe: all four impls agree to 8 digits)."""
+    return [_siglip_loss_one_rank(r, image_features, text_features, logit_scale, logit_bias)
+            for r in range(len(image_features))]
+
+
+def siglip_loss_rank_grads(image_features, text_features, logit_scale, logit_bias, rank: int):
+    """(loss_rank, d image_features[rank], d text_features[rank], d logit_scale, d logit_bias) as ONE rank of the
+    reference sees them: feature gradients of the sum of all ranks' losses (the exchanges carry autograd,
+    loss.py:226-311), scalar gradients of this rank's loss."""
     W = len(image_features)
-    out = []
+    img = [f.detach() for f in image_features]
+    txt = [f.detach() for f in text_features]
+    img[rank] = img[rank].clone().requires_grad_(True)
+    txt[rank] = txt[rank].clone().requires_grad_(True)
+    out = None
     for r in range(W):
-        loss = siglip_block_loss(image_features[r], text_features[r], logit_scale, logit_bias)
-        for s in range(W):
-            if s != r:
-                loss = loss + siglip_block_loss(image_features[r], text_features[s], logit_scale, logit_bias, True)
-        out.append(loss)
-    return out
+        scale = logit_scale.detach().clone().requires_grad_(True)
+        bias = logit_bias.detach().clone().requires_grad_(True)
+        loss = _siglip_loss_one_rank(r, img, txt, scale, bias)
+        loss.backward()
+        if r == rank:
+            out = (loss.detach(), scale.grad.detach(), bias.grad.detach())
+    return out[0], img[rank].grad, txt[rank].grad, out[1], out[2]
 
 
 # --------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ What it does
      the reference CLIP, runs reference forward + reference loss + backward, and
      asserts the oracle restatement reproduces features / loss / every parameter gradient;
   3. runs the reference ClipLoss / SigLipLoss under a real gloo process group (W=2,4) and
-     asserts the process-group-free restatement in clip_oracle reproduces values and
+     asserts (W=2,4,8) the process-group-free restatement in clip_oracle reproduces values and
      feature gradients;
   4. writes the reference outputs as fixtures (features, losses, per-parameter gradient
      probes) that tests/ compare the oracle (CPU suite) and the CUDA path (GPU suite) to.
@@ -201,7 +201,7 @@ def main():
     open_clip = _import_reference()
     gold_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold_dir, exist_ok=True)
-    only = sys.argv[1:] or ["tiny", "vitb32", "vitl14", "vitb16_siglip", "loss"]
+    only = sys.argv[1:] or ["tiny", "vitb32", "vitl14", "vitl14_full", "vitb16_siglip", "loss"]
     if "tiny" in only:
         print("model goldens: tiny")
         torch.save(model_goldens(open_clip, "tiny", batch=8, seed=1, keep_full_grads=False),
@@ -213,11 +213,16 @@ def main():
         print("model goldens: ViT-L-14-336 geometry, depth 2+2")
         torch.save(model_goldens(open_clip, "ViT-L-14-336-d2", batch=8, seed=11),
                    os.path.join(gold_dir, "vitl14_336_d2_model.pt"))
+    if "vitl14_full" in only:
+        # BASELINE config 4 at its real depth (24 + 12 blocks), batch 2: minutes of reference autograd on the CPU
+        print("model goldens: ViT-L-14-336, full depth")
+        torch.save(model_goldens(open_clip, "ViT-L-14-336", batch=2, seed=13),
+                   os.path.join(gold_dir, "vitl14_336_full_model.pt"))
     if "vitb16_siglip" in only:
         print("model goldens: ViT-B-16 + SigLipLoss")
         torch.save(model_goldens(open_clip, "ViT-B-16", batch=8, seed=3, siglip=True),
                    os.path.join(gold_dir, "vitb16_siglip_model.pt"))
-    for w in ((2, 4) if "loss" in only else ()):
+    for w in ((2, 4, 8) if "loss" in only else ((8,) if "loss8" in only else ())):
         print(f"loss goldens: world={w}")
         torch.save(loss_goldens(w), os.path.join(gold_dir, f"loss_w{w}.pt"))
     print("done")

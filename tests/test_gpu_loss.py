@@ -18,9 +18,20 @@ def _feats(b, e, seed):
     return i, t
 
 
-@pytest.mark.parametrize("b,e", [(8, 64), (32, 64), (128, 128), (200, 512), (1000, 512), (4096, 512)])
+@pytest.fixture(params=["fused", "generic"])
+def path(request, monkeypatch):
+    """fused = the peer-streaming kernel (stationary column tile; what multi-rank runs use, here with one rank);
+    generic = the fallback for shapes outside its envelope (M-major tcgen05 GEMM with the same epilogues)."""
+    if request.param == "generic":
+        from open_clip_b200 import ops
+        monkeypatch.setattr(ops, "peer_gemm_tile_n", lambda world, b, e: 0)
+    return request.param
+
+
+@pytest.mark.parametrize("b,e", [(8, 64), (32, 64), (128, 128), (200, 512), (1000, 512), (4096, 512), (520, 768),
+                                 (256, 1024), (64, 32)])
 @pytest.mark.parametrize("feat_dtype", [BF16, F32])
-def test_clip_loss_value_and_grads(b, e, feat_dtype):
+def test_clip_loss_value_and_grads(b, e, feat_dtype, path):
     i, t = _feats(b, e, 3)
     scale = torch.tensor(14.2857, device="cuda")
     gi, gt = i.clone().to(feat_dtype).requires_grad_(True), t.clone().to(feat_dtype).requires_grad_(True)
@@ -38,8 +49,37 @@ def test_clip_loss_value_and_grads(b, e, feat_dtype):
     assert abs(float(gs.grad) - float(rs.grad)) < 1e-2 * abs(float(rs.grad)) + 1e-5
 
 
-@pytest.mark.parametrize("b,e", [(64, 32), (256, 512)])
-def test_siglip_loss_value_and_grads(b, e):
+def test_clip_loss_large_logit_scale():
+    """logit_scale at its clamp (100, image_text_task.py:98-101): the online LSE must not over/underflow."""
+    b, e = 512, 512
+    i, t = _feats(b, e, 9)
+    t = F.normalize(t.float() + 0.5 * i.float(), dim=-1).to(BF16)  # make the positives stand out a little
+    scale = torch.tensor(100.0, device="cuda")
+    gi, gt, gs = i.clone().requires_grad_(True), t.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+    loss = NativeClipLoss()(gi, gt, gs)
+    loss.backward()
+    ri, rt = i.float().cpu().requires_grad_(True), t.float().cpu().requires_grad_(True)
+    rs = scale.cpu().clone().requires_grad_(True)
+    rl = O.clip_loss(ri, rt, rs)
+    rl.backward()
+    assert torch.isfinite(loss) and abs(float(loss) - float(rl)) < 3e-2 + 1e-2 * abs(float(rl))
+    assert rel_err(gi.grad.cpu(), ri.grad) < 1.5e-2 and rel_err(gt.grad.cpu(), rt.grad) < 1.5e-2
+
+
+def test_siglip_no_grad_forward_skips_the_gradient_gemms():
+    from open_clip_b200 import ops
+    i, t = _feats(256, 512, 5)
+    scale, bias = torch.tensor(10.0, device="cuda"), torch.tensor(-10.0, device="cuda")
+    ops.LAUNCHES = 0
+    with torch.no_grad():
+        l0 = NativeSigLipLoss()(i.clone().requires_grad_(True), t, scale, bias)
+    assert ops.LAUNCHES == 1  # one fused launch: no d(logits), no d(feature) GEMMs
+    l1 = NativeSigLipLoss()(i.clone().requires_grad_(True), t, scale, bias)
+    assert abs(float(l0) - float(l1)) < 1e-3 * abs(float(l1)) + 1e-4
+
+
+@pytest.mark.parametrize("b,e", [(64, 32), (256, 512), (200, 128), (1000, 512)])
+def test_siglip_loss_value_and_grads(b, e, path):
     i, t = _feats(b, e, 5)
     scale, bias = torch.tensor(10.0, device="cuda"), torch.tensor(-10.0, device="cuda")
     gi, gt = i.clone().requires_grad_(True), t.clone().requires_grad_(True)

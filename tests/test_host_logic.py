@@ -41,7 +41,42 @@ def _emulate_rank(rank, img, txt, scale, local_loss, gwg):
     return value, scale * d1 @ all_t, scale * d2 @ all_i
 
 
-@pytest.mark.parametrize("world", [2, 4])
+def _emulate_siglip_rank(rank, img, txt, scale, bias):
+    """Pure-torch emulation of NativeSigLipLoss on one rank: direction 0 (my image rows x ALL text columns, one
+    positive per row) gives the value and d_img; direction 1 (my text rows x ALL image columns) gives d_txt with no
+    reverse exchange — a SigLIP logit's gradient depends only on the pair."""
+    W, B = len(img), img[0].shape[0]
+    all_i, all_t = torch.cat(img), torch.cat(txt)
+    idx = torch.arange(B)
+
+    def direction(rows, cols):
+        z = scale * rows @ cols.T + bias
+        y = -torch.ones(B, W * B)
+        y[idx, rank * B + idx] = 1.0
+        loss = -torch.nn.functional.logsigmoid(y * z).sum() / B
+        dz = -y * torch.sigmoid(-y * z) / B
+        return loss, dz
+    value, dz0 = direction(img[rank], all_t)
+    _, dz1 = direction(txt[rank], all_i)
+    return value, scale * dz0 @ all_t, scale * dz1 @ all_i
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_siglip_two_direction_formulation_reproduces_reference_gradients(golden_dir, world):
+    gold = torch.load(os.path.join(golden_dir, f"loss_w{world}.pt"), weights_only=False)
+    f = gold["feats"]
+    for case in gold["cases"]:
+        if case["kind"] != "siglip":
+            continue
+        for r in range(world):
+            value, d_img, d_txt = _emulate_siglip_rank(r, f["img"], f["txt"], f["scale"], f["bias"])
+            ref = case["ranks"][r]
+            assert abs(float(value) - ref["loss"]) < 1e-4, (case["kwargs"], r)
+            assert (d_img - ref["d_img"]).abs().max() < 1e-6, (case["kwargs"], r)
+            assert (d_txt - ref["d_txt"]).abs().max() < 1e-6, (case["kwargs"], r)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_lse_exchange_formulation_reproduces_reference_gradients(golden_dir, world):
     gold = torch.load(os.path.join(golden_dir, f"loss_w{world}.pt"), weights_only=False)
     f = gold["feats"]
@@ -76,6 +111,11 @@ def test_bench_helpers_aggregate_without_a_gpu():
     c1, c8 = bench.workload_config("ViT-B-32", 4096, 1), bench.workload_config("ViT-B-32", 4096, 8)
     assert "local batch 4096, 1xB200" in c1["workload"] and c1["global_batch"] == 4096
     assert c8["global_batch"] == 32768 and c8["parallelism"] == "dp8" and "gather" in c8["workload"]
+    c5 = bench.workload_config("ViT-B-16", 2048, 8, siglip=True)
+    assert "SigLipLoss" in c5["workload"] and c5["global_batch"] == 16384
+    # the reference arm names what it really runs (fp32, batch 32, CPU threads), not the native workload
+    cr = bench.reference_config(32, 16, 1)
+    assert "fp32, batch 32, CPU 16 threads" in cr["workload"] and cr["global_batch"] == 32
 
 
 def test_grad_checkpointing_schedule(monkeypatch):

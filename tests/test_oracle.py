@@ -56,6 +56,7 @@ def test_vitb32_fp32_features_match_reference_fixture(golden_dir):
 
 
 @pytest.mark.parametrize("fixture,cfg_name", [("vitl14_336_d2_model.pt", "ViT-L-14-336-d2"),
+                                              ("vitl14_336_full_model.pt", "ViT-L-14-336"),  # config 4 at 24 + 12 blocks
                                               ("vitb16_siglip_model.pt", "ViT-B-16")])
 def test_other_baseline_geometries_match_reference_fixture(golden_dir, fixture, cfg_name):
     """BASELINE config 4 geometry (patch 14, 577 tokens, widths 1024/768; depth 2+2) with ClipLoss and config 5
@@ -95,7 +96,28 @@ def test_clip_loss_is_invariant_to_logit_bias():
     assert abs(float(gb)) < 1e-12 and (gi - gi0).abs().max() < 1e-12
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_per_rank_gradient_view_matches_gloo_reference_fixture(golden_dir, world):
+    """clip_loss_rank_grads / siglip_loss_rank_grads (the memory-lean per-rank view bench.py's parity block and the
+    multi-GPU tests use) against the outputs of the REAL reference under gloo, every rank, every mode."""
+    gold = _load(golden_dir, f"loss_w{world}.pt")
+    f = gold["feats"]
+    for case in gold["cases"]:
+        for r in range(world):
+            want = case["ranks"][r]
+            if case["kind"] == "clip":
+                kw = case["kwargs"]
+                v, di, dt, ds = O.clip_loss_rank_grads(f["img"], f["txt"], f["scale"], r, kw["local_loss"],
+                                                       kw["gather_with_grad"])
+            else:
+                v, di, dt, ds, db = O.siglip_loss_rank_grads(f["img"], f["txt"], f["scale"], f["bias"], r)
+                assert abs(float(db) - want["d_bias"]) < 1e-4 * max(1.0, abs(want["d_bias"]))
+            assert abs(float(v) - want["loss"]) < 1e-5
+            assert (di - want["d_img"]).abs().max() < 1e-6 and (dt - want["d_txt"]).abs().max() < 1e-6
+            assert abs(float(ds) - want["d_scale"]) < 1e-4 * max(1.0, abs(want["d_scale"]))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_multi_rank_losses_match_gloo_reference_fixture(golden_dir, world):
     gold = _load(golden_dir, f"loss_w{world}.pt")
     f = gold["feats"]
