@@ -61,9 +61,13 @@ enum clipn_epilogue {
   CLIPN_EPI_LSE = 6,        /* no C.  Online row log-sum-exp partials of alpha*acc (+logit_bias):
                                part_max/part_sum[(n_tile*2+half)*M + m], and the label logit
                                (column == m + label_offset) into pos[m]  (ClipLoss fwd, loss.py:102-139)   */
-  CLIPN_EPI_CLIP_DLOGITS = 7, /* C(bf16)[m,n] = gscale*( exp(s-row_lse[m]) + exp(s-col_lse[n])*col_w
-                               - (1+col_w)*[n == m+label_offset] ), s = alpha*acc (+logit_bias);
-                               also accumulates d(loss)/d(logit_scale) (ClipLoss bwd)                     */
+  CLIPN_EPI_CLIP_DLOGITS = 7, /* C(bf16)[m,n] = gscale*( exp(s-row_lse[m]) + col_w*exp(s-col_lse[n]) - (1+col_w)/N ),
+                               s = alpha*acc (+logit_bias): the softmax parts of d loss / d logits, centred on their
+                               mean.  The caller restores the mean and the one-hot part
+                               -(1+col_w)*gscale*[n == m+label_offset] in fp32 (bf16 would lose 2^-9 of values
+                               ~1/N resp. ~2, which dominates the gradient while the features are nearly parallel).
+                               Also accumulates scalar_acc[0] += gscale * sum (P_row - onehot) * acc
+                               (d loss / d logit_scale)                                                    */
   CLIPN_EPI_SIGLIP = 8,     /* softplus / sigmoid epilogue for SigLipLoss (loss.py:351-367): see
                                clipn_siglip_* below                                                       */
   CLIPN_EPI_BIAS_GELU_GRAD = 9, /* t = bf16(acc + bias); C = bf16(gelu'(t)); C2 = bf16(gelu_erf(t)): the forward
@@ -218,13 +222,15 @@ int64_t clipn_clip_lse_workspace(int32_t m, int32_t n);
 int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e, float scale,
                        const float* scale_dev, int32_t label_offset, float* lse, float* pos, float* workspace,
                        clipn_stream_t stream);
-/* dlogits (bf16 [m, ld]) for one direction, see CLIPN_EPI_CLIP_DLOGITS; col_lse is the OTHER direction's
- * global LSE vector [n] (all ranks), scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
+/* dlogits (bf16 [m, ld]) for one direction, mean-centred and WITHOUT the one-hot term, see CLIPN_EPI_CLIP_DLOGITS;
+ * col_lse is the OTHER direction's global LSE vector [n] (all ranks),
+ * scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
 int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e, float scale,
                        const float* scale_dev, int32_t label_offset, const float* row_lse, const float* col_lse,
                        float col_w, float gscale, void* dlogits, int64_t ld, float* scalar_acc, clipn_stream_t stream);
-/* d_rows (fp32 [m,E], zeroed by the caller) += alpha * dlogits[m,n] @ feats_cols[n,E]; split-K over n in `splits`
- * chunks (TMA reduce-add) so that the [m x E] output fills the machine. */
+/* d_rows (fp32 [m,E]) += alpha * dlogits[m,n] @ feats_cols[n,E]; split-K over n in `splits` chunks (TMA reduce-add)
+ * so that the [m x E] output fills the machine.  The caller initialises d_rows: zeros, or for ClipLoss the fp32 part
+ * (1+col_w) * gscale * alpha * (mean_n feats_cols[n] - feats_cols[label_offset + m]). */
 int clipn_clip_dfeat(const void* dlogits, int64_t ld, const void* feats_cols, int32_t m, int32_t n, int32_t e,
                      float alpha, const float* alpha_dev, float* d_rows, int32_t splits, clipn_stream_t stream);
 

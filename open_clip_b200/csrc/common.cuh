@@ -83,11 +83,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU box.
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU box.  try_wait itself suspends the
+// thread for a hardware-defined time; the clock is read once per 64 polls so the single-lane producer / MMA warps do
+// not flood the issue slots they share with the epilogue warps (CS2R + IADD + ISETP per poll showed up as ~2
+// instructions per output element in the GELU GEMMs, profiles/r02_ncu_gelugrad_before.txt).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i)
+      if (mbar_try_wait(bar, parity)) return;
     if (clock64() - t0 > CLIPN_WAIT_CYCLES) {  // ~5 s at 2 GHz: a legitimate wait is micro- to milliseconds
       printf("clipn: mbarrier wait timed out (block %d thread %d bar %p parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, (void*)bar, parity);
@@ -330,6 +336,61 @@ __device__ __forceinline__ void gelu_and_grad(float x, float& gelu, float& grad)
   gelu_core(x, c, g);
   gelu = x * c;
   grad = fmaf(x * 0.3989422804014327f, g, c);
+}
+
+// ---- packed fp32 pairs: sm_100 executes fma / mul / add on two fp32 values per issue slot (FFMA2 / FMUL2 / FADD2).
+// The fused epilogues are issue-bound (ncu: 8 FFMA + 5 FMUL per element in the GELU epilogue), so every elementwise
+// step works on the register pairs tcgen05.ld delivers.
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_splat(float c) { return f2_pack(c, c); }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// round two fp32 values to bf16 and back (one F2FP pack + two bit ops instead of two convert round trips)
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xffff0000u);
+}
+// gelu_core on a pair: 8 FFMA2/FMUL2 + ... per TWO elements; same formula, same constants, same rounding per lane.
+template <bool kGrad>
+__device__ __forceinline__ void gelu_pair(float x0, float x1, float& gl0, float& gl1, float& gr0, float& gr1) {
+  const f32x2 x = f2_pack(x0, x1);
+  const f32x2 den = f2_fma(f2_splat(0.3275911f * 0.70710678118654752f), f2_pack(fabsf(x0), fabsf(x1)), f2_splat(1.0f));
+  float d0, d1;
+  f2_unpack(den, d0, d1);
+  const f32x2 t = f2_pack(rcp_approx(d0), rcp_approx(d1));
+  float a0, a1;
+  f2_unpack(f2_mul(f2_mul(x, x), f2_splat(-0.72134752044448170f)), a0, a1);
+  const f32x2 gauss = f2_pack(ex2_approx(a0), ex2_approx(a1));
+  f32x2 p = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));  // -(a5 t + a4) ... negated Horner chain
+  p = f2_fma(p, t, f2_splat(-1.421413741f));
+  p = f2_fma(p, t, f2_splat(0.284496736f));
+  p = f2_fma(p, t, f2_splat(-0.254829592f));
+  const f32x2 erf_abs = f2_fma(f2_mul(p, t), gauss, f2_splat(1.0f));  // 1 - (a1 t + ... + a5 t^5) e^{-z^2}
+  const f32x2 c = f2_fma(f2_pack(copysignf(0.5f, x0), copysignf(0.5f, x1)), erf_abs, f2_splat(0.5f));
+  f2_unpack(f2_mul(x, c), gl0, gl1);
+  if (kGrad) f2_unpack(f2_fma(f2_mul(x, f2_splat(0.3989422804014327f)), gauss, c), gr0, gr1);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -53,12 +53,13 @@ template <int BN, int EPI, int CTAS>
 struct TileCfg {
   static constexpr int B_STAGE_BYTES = (BN / CTAS) * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  // Pair kernel, dual-output epilogues (GELU fwd / bwd): per warp 6 x 2 KB tiles (32 rows x 32 cols, SW64):
-  // out0, out1 and aux, each double-buffered, so the TMA stores of piece i and the aux TMA load of piece i+1
-  // overlap the math of piece i.  Otherwise: kBufs x 4 KB (32 rows x 64 cols, SW128), single-buffered.
-  static constexpr bool kPipedEpi = CTAS == 2 && EpiTraits<EPI>::kNumOut == 2;
+  // Pair kernel, GELU fwd / bwd epilogues (two outputs, or one output x one operand): per warp 2 KB tiles
+  // (32 rows x 32 cols, SW64) — each output and the aux operand double-buffered — so the TMA stores of piece i and the
+  // aux TMA load of piece i+1 overlap the math of piece i.  Otherwise: kBufs x 4 KB (32 rows x 64 cols, SW128).
+  static constexpr bool kPipedEpi = CTAS == 2 && (EpiTraits<EPI>::kNumOut == 2 || EPI == CLIPN_EPI_MUL_AUX);
+  static constexpr int PIPE_TILES = 2 * EpiTraits<EPI>::kNumOut + (EpiTraits<EPI>::kAux ? 2 : 0);  // 4 or 6
   static constexpr int EPI_BYTES =
-      kPipedEpi ? kEpiWarps * 6 * 2048 : kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 / 64 / 96 KB
+      kPipedEpi ? kEpiWarps * PIPE_TILES * 2048 : kEpiWarps * EpiTraits<EPI>::kBufs * EPI_BUF_BYTES;  // 0 / 32 / 64 / 96 KB
   static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
   static constexpr int STAGES_FIT = (BUDGET - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -175,13 +176,15 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
   const bool row_ok = row < p.m;
   const int nvalid = (p.n - col) < 32 ? (p.n - col) : 32;
   if constexpr (EPI == CLIPN_EPI_STORE || EPI == CLIPN_EPI_STORE_F32) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;
+    const f32x2 al = f2_splat(p.alpha);
     if (p.bias != nullptr) {
       float b[32];
       load_bias32(p.bias, col, b, nvalid);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += b[i];
+      for (int i = 0; i < 32; i += 2) f2_unpack(f2_fma(f2_pack(v[i], v[i + 1]), al, f2_pack(b[i], b[i + 1])), v[i], v[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) f2_unpack(f2_mul(f2_pack(v[i], v[i + 1]), al), v[i], v[i + 1]);
     }
     if constexpr (EPI == CLIPN_EPI_STORE_F32) {
       if (row_ok) {
@@ -195,37 +198,45 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      v[i] = bf16_round(v[i] + b[i]);
-      o1[i] = gelu_exact(v[i]);
+    for (int i = 0; i < 32; i += 2) {
+      f2_unpack(f2_add(f2_pack(v[i], v[i + 1]), f2_pack(b[i], b[i + 1])), v[i], v[i + 1]);
+      bf16_round2(v[i], v[i + 1]);
+      float u0, u1;
+      gelu_pair<false>(v[i], v[i + 1], o1[i], o1[i + 1], u0, u1);
     }
   } else if constexpr (EPI == CLIPN_EPI_BIAS_GELU_GRAD) {
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float t = bf16_round(v[i] + b[i]);
-      gelu_and_grad(t, o1[i], v[i]);  // C2 = gelu(t), C = gelu'(t)
+    for (int i = 0; i < 32; i += 2) {
+      float t0, t1;
+      f2_unpack(f2_add(f2_pack(v[i], v[i + 1]), f2_pack(b[i], b[i + 1])), t0, t1);
+      bf16_round2(t0, t1);
+      gelu_pair<true>(t0, t1, o1[i], o1[i + 1], v[i], v[i + 1]);  // C2 = gelu(t), C = gelu'(t)
     }
   } else if constexpr (EPI == CLIPN_EPI_MUL_AUX) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= aux[i];
+    for (int i = 0; i < 32; i += 2) f2_unpack(f2_mul(f2_pack(v[i], v[i + 1]), f2_pack(aux[i], aux[i + 1])), v[i], v[i + 1]);
   } else if constexpr (EPI == CLIPN_EPI_BIAS_RESID) {
     float b[32];
     load_bias32(p.bias, col, b, nvalid);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i] + b[i]) + aux[i];
+    for (int i = 0; i < 32; i += 2) {
+      f2_unpack(f2_add(f2_pack(v[i], v[i + 1]), f2_pack(b[i], b[i + 1])), v[i], v[i + 1]);
+      bf16_round2(v[i], v[i + 1]);
+      f2_unpack(f2_add(f2_pack(v[i], v[i + 1]), f2_pack(aux[i], aux[i + 1])), v[i], v[i + 1]);
+    }
   } else if constexpr (EPI == CLIPN_EPI_DGELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float gl, gr;
-      gelu_and_grad(aux[i], gl, gr);
-      v[i] = v[i] * gr;
-      o1[i] = gl;
+    for (int i = 0; i < 32; i += 2) {
+      float g0, g1;
+      gelu_pair<true>(aux[i], aux[i + 1], o1[i], o1[i + 1], g0, g1);
+      f2_unpack(f2_mul(f2_pack(v[i], v[i + 1]), f2_pack(g0, g1)), v[i], v[i + 1]);
     }
   } else if constexpr (EPI == CLIPN_EPI_ACCUM_F32) {
+    const f32x2 al = f2_splat(p.alpha);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= p.alpha;  // reduce-added to C by the caller (TMA in the tensor-core path)
+    for (int i = 0; i < 32; i += 2) f2_unpack(f2_mul(f2_pack(v[i], v[i + 1]), al), v[i], v[i + 1]);  // reduce-added to C by the caller
   } else if constexpr (EPI == CLIPN_EPI_LSE) {
     // online log-sum-exp in the log2 domain: t = (alpha*acc + bias) * log2(e); one FFMA + FMNMX + FADD + MUFU.EX2 +
     // FADD per element (raw ex2.approx: the range-checked exp2f() costs ~6 more issue slots per element and this
@@ -281,6 +292,7 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
         cl2[4 * i] = t.x * kLog2e; cl2[4 * i + 1] = t.y * kLog2e; cl2[4 * i + 2] = t.z * kLog2e; cl2[4 * i + 3] = t.w * kLog2e;
       }
     }
+    const float shift = (1.f + p.col_w) / static_cast<float>(p.n);
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -289,12 +301,12 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
       float pr = ex2_approx(s2 - rl2);
       float pc = (p.col_w != 0.f) ? p.col_w * ex2_approx(s2 - cl2[i]) : 0.f;
       if (i >= nvalid) { pr = 0.f; pc = 0.f; }
-      float g = pr + pc;
-      if (has_label && col + i == label) {
-        g -= 1.f + p.col_w;
-        pr -= 1.f;
-      }
-      v[i] = p.gscale * g;
+      // C holds the softmax parts CENTRED on their mean (1 + col_w) / N, without the one-hot of the label column: bf16
+      // then rounds the deviation from the uniform distribution instead of values ~1/N (and never a value ~2 next to
+      // them), which is what keeps d(features) accurate while the features are still nearly parallel (fresh model).
+      // The caller restores both parts in fp32: (1 + col_w) * gscale * alpha * (mean_n cols[n] - cols[label]).
+      v[i] = p.gscale * (pr + pc - shift);
+      if (has_label && col + i == label) pr -= 1.f;
       a0 = fmaf(pr, dot, a0);
       a1 += pr;
     }
@@ -738,7 +750,7 @@ static int launch_ref(const GemmParams& p, const RefOperands& ops, int bn, cudaS
 
 int peer_gemm_tile_n(int world, int rows_per_map, int e) {
   if (e <= 0 || e % BK != 0 || e > 1024 || world < 1 || world > kMaxBMaps || rows_per_map <= 0) return 0;
-  const int bn = e <= 512 ? 128 : 64;
+  const int bn = e <= 512 ? 256 : 128;
   if (world > 1 && rows_per_map % bn != 0) return 0;  // a column tile must not straddle two ranks' buffers
   return bn;
 }
@@ -777,7 +789,8 @@ int peer_gemm_launch(const PeerGemmDesc& d, cudaStream_t stream) {
   CLIPN_REQUIRE(d.m > 0, "peer gemm: empty problem");
   const int bn = peer_gemm_tile_n(d.world, d.rows_per_map, d.e);
   CLIPN_REQUIRE(bn != 0,
-                "peer gemm: needs embed dim % 64 == 0 and <= 1024, world <= 8, per-rank rows % 128 == 0 when world > 1");
+                "peer gemm: needs embed dim % 64 == 0 and <= 1024, world <= 8, per-rank rows % 256 == 0 (128 for embed dim > "
+                "512) when world > 1");
   int cc_major = 0, sms = 0, cc_minor = 0;
   clipn_device_info(&sms, &cc_major, &cc_minor);
   CLIPN_REQUIRE(cc_major == 10, "peer gemm: the tcgen05 kernels require an sm_100 (B200) device");
@@ -825,8 +838,8 @@ int peer_gemm_launch(const PeerGemmDesc& d, cudaStream_t stream) {
     for (int dir = 0; dir < d.dirs; ++dir)
       CLIPN_REQUIRE(d.gather[dir] != nullptr, "peer gemm: gather buffers must be given for every direction or none");
   if (d.epilogue == CLIPN_EPI_LSE)
-    return bn == 128 ? launch_peer<128, CLIPN_EPI_LSE>(tm, p, stream) : launch_peer<64, CLIPN_EPI_LSE>(tm, p, stream);
-  return bn == 128 ? launch_peer<128, CLIPN_EPI_SIGLIP>(tm, p, stream) : launch_peer<64, CLIPN_EPI_SIGLIP>(tm, p, stream);
+    return bn == 256 ? launch_peer<256, CLIPN_EPI_LSE>(tm, p, stream) : launch_peer<128, CLIPN_EPI_LSE>(tm, p, stream);
+  return bn == 256 ? launch_peer<256, CLIPN_EPI_SIGLIP>(tm, p, stream) : launch_peer<128, CLIPN_EPI_SIGLIP>(tm, p, stream);
 }
 
 #define CLIPN_DISPATCH_EPI(EPIVAR, MACRO)                                   \
@@ -936,7 +949,7 @@ int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps,
                        ep == CLIPN_EPI_DGELU || ep == CLIPN_EPI_CLIP_DLOGITS || (ep == CLIPN_EPI_SIGLIP && d.c != nullptr) ||
                        ep == CLIPN_EPI_BIAS_GELU_GRAD || ep == CLIPN_EPI_MUL_AUX;
   // pair kernel + two-output epilogue: 32-column pieces (64-byte rows, SW64), see TileCfg::kPipedEpi
-  const bool piped = use_pair && two_out;
+  const bool piped = use_pair && (two_out || ep == CLIPN_EPI_MUL_AUX);
   const uint32_t ebox = piped ? 32 : 64;
   const int esw = piped ? 64 : 128;
   if (out_tma) {

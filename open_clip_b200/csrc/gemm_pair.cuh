@@ -153,7 +153,9 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       // ---- software-pipelined epilogue for the two-output GELU variants: 32-column pieces, double-buffered
       // staging; piece i's TMA stores and piece i+1's aux TMA load are in flight while piece i is computed ----
       constexpr int NP = BN / 64;  // pieces per warp per tile
-      uint8_t* wb = epi_smem + e * (6 * 2048);
+      constexpr int OUT1 = 4096;                  // second output's tiles (two-output epilogues)
+      constexpr int AUX = Tr::kNumOut * 4096;     // aux operand's tiles
+      uint8_t* wb = epi_smem + e * (Cfg::PIPE_TILES * 2048);
       uint64_t* abar = aux_bar + 2 * e;
       auto coords = [&](int w, int i, int& col, int& row0) {
         const int tile = w / p.splits;
@@ -165,7 +167,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
         int col, row0;
         coords(cluster_id, 0, col, row0);
         mbar_expect_tx(&abar[0], 2048);
-        tma_load_2d(wb + 8192, &tm.aux, &abar[0], col, row0);
+        tma_load_2d(wb + AUX, &tm.aux, &abar[0], col, row0);
       }
       int acc = 0;
       uint32_t acc_phase = 0;
@@ -192,23 +194,23 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
                 int ncol, nrow0;
                 coords(nw, ni, ncol, nrow0);
                 mbar_expect_tx(&abar[b ^ 1], 2048);
-                tma_load_2d(wb + 8192 + (b ^ 1) * 2048, &tm.aux, &abar[b ^ 1], ncol, nrow0);
+                tma_load_2d(wb + AUX + (b ^ 1) * 2048, &tm.aux, &abar[b ^ 1], ncol, nrow0);
               }
             }
             mbar_wait(&abar[b], (pc >> 1) & 1);
           }
           float v[32], aux[32], o1[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + h * (BN / 2) + i * 32, v);
-          if (Tr::kAux) stage64_read32(wb + 8192 + b * 2048, lane, aux);
+          if (Tr::kAux) stage64_read32(wb + AUX + b * 2048, lane, aux);
           if (col < p.n) epi_compute<EPI>(p, row0 + lane, col, v, aux, o1, st);
           stage64_write32(wb + b * 2048, lane, v);
-          if (p.c2 != nullptr) stage64_write32(wb + 4096 + b * 2048, lane, o1);
-          if (EPI == CLIPN_EPI_DGELU && p.col_sum != nullptr && col < p.n) epi_col_sum(p, row0 + lane, col, v);
+          if (Tr::kNumOut == 2 && p.c2 != nullptr) stage64_write32(wb + OUT1 + b * 2048, lane, o1);
+          if (Tr::kColSum && p.col_sum != nullptr && col < p.n) epi_col_sum(p, row0 + lane, col, v);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(&tm.c, wb + b * 2048, col, row0);  // boxes past N / M are clipped by the TMA unit
-            if (p.c2 != nullptr) tma_store_2d(&tm.c2, wb + 4096 + b * 2048, col, row0);
+            if (Tr::kNumOut == 2 && p.c2 != nullptr) tma_store_2d(&tm.c2, wb + OUT1 + b * 2048, col, row0);
             tma_store_commit();
           }
         }

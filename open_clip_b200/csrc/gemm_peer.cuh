@@ -5,10 +5,15 @@
 //   S_d[m, c] = rows_d[m, :] . cols_d[c, :]      d = 0: local image rows x every rank's text rows
 //                                                d = 1: local text rows  x every rank's image rows
 //
-// Why a dedicated kernel: with K = embed_dim <= 512 the whole column tile (BN rows x K) fits in shared memory, so the
-// COLUMN operand — the one that lives in the other ranks' HBM — is the stationary operand: a CTA pair pulls a
-// [BN x K] tile from the owning rank's symmetric buffer through that rank's TMA tensor map exactly once
-// (NVLink / NVSwitch P2P), double-buffered, and streams the local row operand past it out of L2 (4 MB, resident).
+// Why a dedicated kernel: with K = embed_dim <= 512 the whole column tile (BN = 256 rows x K: 128 KB per CTA of the
+// pair) fits in shared memory, so the COLUMN operand — the one that lives in the other ranks' HBM — is the stationary
+// operand: a CTA pair pulls a [BN x K] tile from the owning rank's symmetric buffer through that rank's TMA tensor
+// map exactly once (NVLink / NVSwitch P2P) and streams the local row operand past it out of L2 (4 MB, resident).
+// The tile is single-buffered but refilled PIECE BY PIECE (one 64-wide k-block at a time): on the last M tile of a
+// column tile every k-block's MMAs release their piece, the next tile's piece is requested at once and has a whole
+// unit of tensor work (4096 cycles) to arrive.  BN = 256 (not 128 with two buffers, the first version): the row
+// operand then needs 32 B/cycle/SM from L2 instead of 64 — the 128-wide version was bound by the latency-bandwidth
+// product of its 96 KB ring (ncu: tensor pipe 52 %, the MMA thread spinning on `full`; profiles/r02_ncu_peer_v1.txt).
 // Every peer byte therefore crosses NVLink once per launch (x ~1.1 for tiles shared by two neighbouring work
 // ranges) instead of once per 256-row M tile as in the M-major walk of gemm_tc2_kernel (16x at local batch 4096).
 // The resident tile is also written to a LOCAL [N, K] copy by TMA store as a by-product (the materialised
@@ -21,8 +26,9 @@
 // Warp roles (384 threads, cluster of 2 CTAs, cta_group::2, M = 256):
 //   warp 0 : TMA producer of the row operand  (A ring, 16 KB stages, both CTAs load their own 128 rows)
 //   warp 1 : MMA issuer (leader CTA)           tcgen05.mma.cta_group::2 kind::f16, D = 256 x BN fp32 in TMEM, x2
-//   warp 2 : TMEM allocator
-//   warp 3 : TMA producer of the column tiles (peer reads) + TMA stores of the gathered copy
+//   warp 2 : TMEM allocator, then relay: as each piece of a column tile lands it TMA-stores it to the gathered
+//            copy and reports it to the leader's `piece_full` barrier
+//   warp 3 : TMA producer of the column-tile pieces (peer reads)
 //   warps 4-7 / 8-11 : epilogue of even / odd units (accumulator 0 / 1): online LSE (CLIP) or softplus/sigmoid (SigLIP)
 #pragma once
 
@@ -51,19 +57,22 @@ struct PeerParams {
 template <int BN, int EPI>
 struct PeerCfg {
   static constexpr int BNH = BN / 2;                   // column-tile rows staged by each CTA of the pair
-  static constexpr int KB_MAX = 8 * 128 / BN;          // 8 k-blocks (K <= 512) at BN = 128, 16 (K <= 1024) at BN = 64
-  static constexpr int B_PIECE = BNH * BK * 2;         // one k-block of the resident tile: 8 KB / 4 KB
-  static constexpr int B_BYTES = 2 * KB_MAX * B_PIECE; // double-buffered resident column tile: 128 KB
+  static constexpr int KB_MAX = 8 * 256 / BN;          // 8 k-blocks (K <= 512) at BN = 256, 16 (K <= 1024) at BN = 128
+  static constexpr int B_PIECE = BNH * BK * 2;         // one k-block of the resident tile: 16 KB / 8 KB
+  static constexpr int B_BYTES = KB_MAX * B_PIECE;     // resident column tile (this CTA's half): 128 KB
   static constexpr int EPI_BYTES = (EPI == CLIPN_EPI_SIGLIP) ? kEpiWarps * EPI_BUF_BYTES : 0;
-  static constexpr int BUDGET = 227 * 1024 - 1024 - 256;
+  static constexpr int BUDGET = 227 * 1024 - 1024 - 640;
   static constexpr int STAGES_FIT = (BUDGET - B_BYTES - EPI_BYTES) / A_STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
+  static constexpr int NUM_BARS = 2 * STAGES + 3 * KB_MAX + 5;
+  static constexpr int BAR_BYTES = NUM_BARS * 8 + 16;
   static constexpr int SMEM_BYTES = B_BYTES + STAGES * A_STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;
   static_assert(STAGES >= 3, "row-operand ring too shallow");
+  static_assert(BAR_BYTES <= 640, "barrier area");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget exceeded");
   static_assert(B_PIECE % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+  static_assert(TMEM_COLS <= 512, "TMEM columns");
 };
 
 template <int BN, int EPI>
@@ -75,14 +84,16 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
   // p stays in the constant bank (its per-direction arrays are indexed dynamically: a local copy would live on the stack)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* bres = smem;                      // [2][KB_MAX] pieces of BNH rows x 64 k (SW128, K-major)
+  uint8_t* bres = smem;                      // [KB_MAX] pieces of BNH rows x 64 k (SW128, K-major)
   uint8_t* aring = smem + Cfg::B_BYTES;      // [STAGES] 128 rows x 64 k
   uint8_t* epi_smem = aring + Cfg::STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + Cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* b_full = empty_bar + Cfg::STAGES;  // leader: both CTAs' column-tile bytes landed
-  uint64_t* b_empty = b_full + 2;              // both CTAs: the MMAs reading this buffer have retired
-  uint64_t* tmem_full = b_empty + 2;
+  uint64_t* b_land = empty_bar + Cfg::STAGES;    // own CTA: this piece's bytes have landed
+  uint64_t* piece_full = b_land + Cfg::KB_MAX;   // leader: both CTAs' halves of this piece are in place
+  uint64_t* piece_empty = piece_full + Cfg::KB_MAX;  // both CTAs: the last MMAs reading this piece have retired
+  uint64_t* st_done = piece_empty + Cfg::KB_MAX; // own CTA: the gathered-copy stores of the tile have left smem
+  uint64_t* tmem_full = st_done + 1;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -104,9 +115,13 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       mbar_init(&full_bar[i], 1);   // leader: one arrive.expect_tx covering both CTAs' bytes (see gemm_pair.cuh)
       mbar_init(&empty_bar[i], 1);  // multicast tcgen05.commit
     }
+    for (int i = 0; i < Cfg::KB_MAX; ++i) {
+      mbar_init(&b_land[i], 1);       // arrive.expect_tx of this CTA's loader
+      mbar_init(&piece_full[i], 2);   // leader: one arrive per CTA (relay threads)
+      mbar_init(&piece_empty[i], 1);  // multicast tcgen05.commit
+    }
+    mbar_init(st_done, 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&b_full[i], 1);
-      mbar_init(&b_empty[i], 1);            // multicast tcgen05.commit
       mbar_init(&tmem_full[i], 1);          // multicast tcgen05.commit
       mbar_init(&tmem_empty[i], kEpiWarps); // leader: 4 epilogue warps of each CTA per accumulator
     }
@@ -125,6 +140,8 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
   const int64_t total_units = static_cast<int64_t>(p.dirs) * p.tiles_n * p.tiles_m;
   const int u0 = static_cast<int>((total_units * cluster_id) / num_clusters);
   const int u1 = static_cast<int>((total_units * (cluster_id + 1)) / num_clusters);
+  const int t_first = u0 < u1 ? u0 / p.tiles_m : 0;        // tile id = d * tiles_n + nt
+  const int t_last = u0 < u1 ? (u1 - 1) / p.tiles_m : -1;
   const int rot = p.rank * (p.rows_per_map / BN);  // column tiles are visited starting at this rank's own block
   auto tile_col0 = [&](int nt) {
     int t = nt + rot;
@@ -154,43 +171,44 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       }
     }
   } else if (warp == 3) {
-    if (elect_one() && u0 < u1) {
-      // ===================== column-tile producer: peer reads + gathered-copy stores (both CTAs) =====================
-      const int t_first = u0 / p.tiles_m, t_last = (u1 - 1) / p.tiles_m;  // tile id = d * tiles_n + nt
-      auto store_tile = [&](int t, int buf) {
-        const int d = t / p.tiles_n;
-        const int n0 = tile_col0(t % p.tiles_n) + static_cast<int>(rank) * BNH;
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_store_2d(&tm.g[d], bres + (buf * Cfg::KB_MAX + kb) * Cfg::B_PIECE, kb * BK, n0);
-        tma_store_commit();
-      };
+    if (elect_one()) {
+      // ===================== column-tile loader: peer reads, one k-block piece at a time (both CTAs) =====================
       for (int t = t_first; t <= t_last; ++t) {
         const int s = t - t_first;
-        const int buf = s & 1;
-        if (s >= 2) {
-          mbar_wait(&b_empty[buf], ((s >> 1) - 1) & 1);  // tile s-2 has been consumed by the tensor core
-          if (p.gather) {
-            store_tile(t - 2, buf);
-            tma_store_wait_read<0>();  // its bytes have left shared memory: the buffer may be overwritten
-          }
-        }
         const int d = t / p.tiles_n;
         const int n0 = tile_col0(t % p.tiles_n);
         const int map = n0 / p.rows_per_map;
         const int r0 = n0 - map * p.rows_per_map + static_cast<int>(rank) * BNH;
-        const uint32_t bar = mapa_u32(smem_u32(&b_full[buf]), 0);
-        if (rank == 0) mbar_expect_tx(&b_full[buf], 2 * p.kblocks * Cfg::B_PIECE);
-        for (int kb = 0; kb < p.kblocks; ++kb)
-          tma_load_2d_2sm(bres + (buf * Cfg::KB_MAX + kb) * Cfg::B_PIECE, &tm.b[d][map], bar, kb * BK, r0);
-      }
-      if (p.gather) {
-        const int ntile = t_last - t_first + 1;
-        for (int s = (ntile > 2 ? ntile - 2 : 0); s < ntile; ++s) {
-          mbar_wait(&b_empty[s & 1], (s >> 1) & 1);
-          store_tile(t_first + s, s & 1);
+        if (s > 0 && p.gather) mbar_wait(st_done, (s - 1) & 1);  // the previous tile's gathered-copy stores have read smem
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (s > 0) mbar_wait(&piece_empty[kb], (s - 1) & 1);   // the previous tile's last MMAs on this piece retired
+          mbar_expect_tx(&b_land[kb], Cfg::B_PIECE);
+          tma_load_2d(bres + kb * Cfg::B_PIECE, &tm.b[d][map], &b_land[kb], kb * BK, r0);
         }
-        tma_store_wait_all<0>();
       }
+    }
+  } else if (warp == 2) {
+    if (elect_one()) {
+      // ===================== relay: landed piece -> gathered copy (TMA store) -> leader's piece_full =====================
+      for (int t = t_first; t <= t_last; ++t) {
+        const int s = t - t_first;
+        const int d = t / p.tiles_n;
+        const int n0 = tile_col0(t % p.tiles_n) + static_cast<int>(rank) * BNH;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(&b_land[kb], s & 1);
+          if (p.gather) {
+            tma_store_2d(&tm.g[d], bres + kb * Cfg::B_PIECE, kb * BK, n0);
+            tma_store_commit();
+          }
+          if (rank == 0) mbar_arrive(&piece_full[kb]);
+          else mbar_arrive_cluster(mapa_u32(smem_u32(&piece_full[kb]), 0));
+        }
+        if (p.gather) {
+          tma_store_wait_read<0>();
+          mbar_arrive(st_done);
+        }
+      }
+      if (p.gather) tma_store_wait_all<0>();
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
@@ -198,23 +216,19 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int cur_tile = -1, seq = -1, buf = 0;
+      const uint32_t sb0 = smem_u32(bres);
       for (int u = u0; u < u1; ++u) {
         const int it = u - u0;
         const int tile = u / p.tiles_m;
-        if (tile != cur_tile) {
-          cur_tile = tile;
-          ++seq;
-          buf = seq & 1;
-          mbar_wait(&b_full[buf], (seq >> 1) & 1);
-          tc_fence_after();
-        }
+        const bool first_of_tile = u == u0 || (u - 1) / p.tiles_m != tile;
+        const bool last_of_tile = u + 1 == u1 || (u + 1) / p.tiles_m != tile;
+        const uint32_t tile_parity = static_cast<uint32_t>(tile - t_first) & 1;
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        const uint32_t sb0 = smem_u32(bres + buf * Cfg::KB_MAX * Cfg::B_PIECE);
         for (int kb = 0; kb < p.kblocks; ++kb) {
+          if (first_of_tile) mbar_wait(&piece_full[kb], tile_parity);
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(aring + stage * A_STAGE_BYTES);
@@ -224,13 +238,13 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
             umma_bf16_2sm(d_tmem, umma_smem_desc(sa + k * 32, 16, 1024), umma_smem_desc(sb + k * 32, 16, 1024), idesc,
                           (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit_2sm(&empty_bar[stage]);
+          if (last_of_tile) umma_commit_2sm(&piece_empty[kb]);  // this piece may be refilled with the next column tile
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
         umma_commit_2sm(&tmem_full[acc]);
-        if (u + 1 == u1 || (u + 1) / p.tiles_m != tile) umma_commit_2sm(&b_empty[buf]);  // last unit of this column tile
       }
     }
   } else if (warp >= 4) {

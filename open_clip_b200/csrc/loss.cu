@@ -33,9 +33,9 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
     float sum = 0.f;
     for (int s = 0; s < slabs; ++s) {
       const float pm = part_max[static_cast<int64_t>(s) * m + row];
-      if (pm != -INFINITY) sum += part_sum[static_cast<int64_t>(s) * m + row] * __expf(pm - mx);
-    }
-    const float l = mx + __logf(sum);
+      if (pm != -INFINITY) sum += part_sum[static_cast<int64_t>(s) * m + row] * expf(pm - mx);  // precise: the
+    }                                                      // backward differentiates through exp(s - lse)
+    const float l = mx + logf(sum);
     lse[row] = l;
     if (pos != nullptr) local = l - pos[dir * dir_stride_vec + row];
   }

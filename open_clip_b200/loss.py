@@ -109,11 +109,18 @@ class _ClipLossFn(torch.autograd.Function):
             all_lse_i, all_lse_t = lse_i, lse_t
         acc = torch.zeros(4, dtype=F32, device=img.device)
         # d logits_per_image[B,N] (rows = my images): row softmax uses my image LSE, column term uses every text's LSE
+        # The bf16 d(logits) tiles hold the softmax parts centred on their mean (1+w)/N and no one-hot; both enter the
+        # fp32 accumulator directly: (1+w) * gscale * scale * (mean of the gathered operand - its row off+m, which is
+        # this rank's own OTHER-modality feature m).  bf16 never rounds a value ~2 or ~1/N, only deviations.
+        N = W * B
+        coef = scale * ((1.0 + col_w) * gscale)  # [1] fp32 device scalar
+        mean_t = ops.colsum(all_txt, torch.zeros(E, dtype=F32, device=img.device)) / N
+        mean_i = ops.colsum(all_img, torch.zeros(E, dtype=F32, device=img.device)) / N
         dl_i = ops.clip_dlogits(img, all_txt, scale, off, lse_i, all_lse_t if col_w else None, col_w, gscale, acc[0:2])
-        d_img = ops.clip_dfeat(dl_i, all_txt, scale)
+        d_img = ops.clip_dfeat(dl_i, all_txt, scale, init=(mean_t - txt.float()) * coef)
         del dl_i
         dl_t = ops.clip_dlogits(txt, all_img, scale, off, lse_t, all_lse_i if col_w else None, col_w, gscale, acc[2:4])
-        d_txt = ops.clip_dfeat(dl_t, all_img, scale)
+        d_txt = ops.clip_dfeat(dl_t, all_img, scale, init=(mean_i - img.float()) * coef)
         del dl_t
         # d loss / d logit_scale = sum_{dir} sum (P_row - onehot) * <row, col> / (2B)   (own loss only)
         d_scale = (acc[0] + acc[2]) * ((1.0 / (2 * B)) / gscale)

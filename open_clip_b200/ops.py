@@ -255,6 +255,7 @@ def colsum(x, out):
     _chk(x, BF16, "colsum.x"); _chk(out, F32, "colsum.out")
     rows, n = x.shape
     _call(L.lib().clipn_colsum(x.data_ptr(), x.stride(0), out.data_ptr(), rows, n, _stream()))
+    return out
 
 
 def cast_f32_to_bf16(x, out=None):
@@ -358,13 +359,16 @@ def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscal
     return out
 
 
-def clip_dfeat(dlogits, cols, alpha: torch.Tensor, n: Optional[int] = None):
-    """fp32 [m, E] = alpha * dlogits[:, :n] @ cols  (split-K over n, TMA reduce-add into a zeroed buffer)."""
+def clip_dfeat(dlogits, cols, alpha: torch.Tensor, n: Optional[int] = None, init: Optional[torch.Tensor] = None):
+    """fp32 [m, E] = init + alpha * dlogits[:, :n] @ cols  (split-K over n, TMA reduce-add into `init` or zeros)."""
     _chk(dlogits, BF16, "dfeat.dlogits"); _chk(cols, BF16, "dfeat.cols")
     m, ld = dlogits.shape
     n = cols.shape[0] if n is None else n
     e = cols.shape[1]
-    out = torch.zeros((m, e), dtype=F32, device=dlogits.device)
+    if init is not None:
+        _chk(init, F32, "dfeat.init")
+        assert tuple(init.shape) == (m, e)
+    out = init if init is not None else torch.zeros((m, e), dtype=F32, device=dlogits.device)
     splits = wgrad_splits(m, e, n)
     with _profiled((m, e, n, L.EPI_ACCUM_F32, False, True)):
         _call(L.lib().clipn_clip_dfeat(dlogits.data_ptr(), ld, cols.data_ptr(), m, n, e, 1.0, alpha.data_ptr(),

@@ -19,4 +19,8 @@ for _ in range(3):
         ops.gemm(x, wpr, b_mn=True, epilogue=L.EPI_DGELU, aux=x4, out=o4, col_sum=cs)
     elif which == "gelu":
         ops.gemm(x, wfc, bias=b4, epilogue=L.EPI_BIAS_GELU, out=o4, out2=o4b)
+    elif which == "gelugrad":  # forward c_fc GEMM of the default (fast) activation mode: writes gelu'(h) and gelu(h)
+        ops.gemm(x, wfc, bias=b4, epilogue=L.EPI_BIAS_GELU_GRAD, out=o4, out2=o4b)
+    elif which == "mulaux":    # backward c_proj dgrad x saved gelu'(h) + fused c_fc bias gradient
+        ops.gemm(x, wpr, b_mn=True, epilogue=L.EPI_MUL_AUX, aux=x4, out=o4, col_sum=cs)
 torch.cuda.synchronize()
