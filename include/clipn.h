@@ -181,6 +181,23 @@ int clipn_l2norm_bwd(const void* dy, int32_t dy_is_f32, const void* y, const flo
 int clipn_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int32_t n, clipn_stream_t stream);
 int clipn_cast_f32_to_bf16(const float* x, void* y, int64_t n, clipn_stream_t stream);
 
+/* ---- optimizer ---------------------------------------------------------------------------------------
+ * Multi-tensor AdamW (decoupled weight decay), one launch for the whole model: replaces torch.optim.AdamW as built by
+ * open_clip_train/optim.py:453-454 (`optimizer.step()`, open_clip_train/train.py:182).  Arithmetic of torch's fused
+ * AdamW: p -= lr*wd*p; m = lerp(m, g, 1-beta1); v = beta2*v + (1-beta2)*g*g;
+ * p -= (lr / bias_correction1) * m / (sqrt(v) / bias_correction2_sqrt + eps), all in fp32, stored back in each tensor's
+ * dtype (bf16 parameters carry bf16 gradients and bf16 moments, as under --precision bf16).  The caller passes the
+ * bias corrections of the current step: 1 - beta1^t and sqrt(1 - beta2^t). */
+#define CLIPN_ADAMW_MAX_TENSORS 512 /* per launch; longer lists are split */
+typedef struct clipn_adamw_tensor {
+  void* param; const void* grad; void* exp_avg; void* exp_avg_sq; /* same dtype, same numel */
+  int64_t numel;
+  float lr, weight_decay;
+  int32_t is_bf16; /* 1: bf16 tensors, 0: fp32 tensors */
+} clipn_adamw_tensor;
+int clipn_adamw_multi(const clipn_adamw_tensor* tensors, int32_t n, float beta1, float beta2, float eps,
+                      float bias_correction1, float bias_correction2_sqrt, clipn_stream_t stream);
+
 /* ---- contrastive losses --------------------------------------------------------------------------
  * ClipLoss (loss.py:57-141) in its local_loss form — this rank's B rows against all N = W*B columns, both
  * directions (logits_per_image rows, logits_per_text rows; loss.py:102-104) — and SigLipLoss (loss.py:314-489).

@@ -38,6 +38,12 @@ class GemmDesc(C.Structure):
     ]
 
 
+class AdamTensor(C.Structure):
+    """Mirror of `struct clipn_adamw_tensor` (include/clipn.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float), ("is_bf16", C.c_int32)]
+
+
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); every symbol include/clipn.h declares
@@ -65,6 +71,7 @@ SIGNATURES = {
     "clipn_l2norm_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _I64, _I32, _P]),
     "clipn_colsum": (C.c_int, [_P, _I64, _P, _I64, _I32, _P]),
     "clipn_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
+    "clipn_adamw_multi": (C.c_int, [C.POINTER(AdamTensor), _I32, _F, _F, _F, _F, _F, _P]),
     "clipn_peer_gemm_tile_n": (_I32, [_I32, _I32, _I32]),
     "clipn_clip_fwd_fused_workspace": (C.c_int64, [_I32, _I32, _I32]),
     "clipn_clip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32, _F,

@@ -209,6 +209,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Same without the release fence (no MEMBAR + ERRBAR): for arrivals that publish no memory — e.g. "my tcgen05.ld of
+// this accumulator have completed" (tcgen05.wait::ld already made the data register-resident).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // TMA load into THIS CTA's smem whose completion bytes are credited to an mbarrier given by cluster address
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr,
                                                 int c_inner, int c_outer) {

@@ -29,7 +29,9 @@
 //   warp 2 : TMEM allocator, then relay: as each piece of a column tile lands it TMA-stores it to the gathered
 //            copy and reports it to the leader's `piece_full` barrier
 //   warp 3 : TMA producer of the column-tile pieces (peer reads)
-//   warps 4-7 / 8-11 : epilogue of even / odd units (accumulator 0 / 1): online LSE (CLIP) or softplus/sigmoid (SigLIP)
+//   warps 4-11 : epilogue, all 8 warps on every unit (TMEM lane quarter x column half): online LSE (CLIP) or
+//                softplus/sigmoid (SigLIP).  (Splitting the warps between the two accumulators doubled the latency of one
+//                unit's epilogue past the 4096-cycle mainloop and stalled the MMA on tmem_empty: 59 % tensor pipe.)
 #pragma once
 
 struct alignas(64) PeerTmaps {
@@ -48,7 +50,7 @@ struct PeerParams {
   const float* alpha_dev;
   const float* logit_bias_dev;
   float* part_max[2];
-  float* part_sum[2];         // LSE: [tiles_n, m] partial sums; SIGLIP: loss accumulator (or null)
+  float* part_sum[2];         // LSE: [2 * tiles_n, m] partial sums; SIGLIP: loss accumulator (or null)
   float* pos[2];
   void* c[2];
   float* scalar_acc[2];
@@ -123,7 +125,7 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
     mbar_init(st_done, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);          // multicast tcgen05.commit
-      mbar_init(&tmem_empty[i], kEpiWarps); // leader: 4 epilogue warps of each CTA per accumulator
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps);  // leader: the 8 epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -248,10 +250,10 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: warps 4-7 own accumulator 0 (even units), warps 8-11 accumulator 1 =====================
+    // ===================== epilogue: 8 warps per unit, warp = (TMEM lane quarter q, column half h) =====================
     const int e = warp - 4;
-    const int q = e & 3;    // TMEM lane quarter == warp % 4
-    const int grp = e >> 2; // accumulator
+    const int q = e & 3;   // TMEM lane quarter == warp % 4
+    const int h = e >> 2;  // column half of the tile
     uint8_t* buf0 = epi_smem + e * EPI_BUF_BYTES;
     GemmParams gp;
     gp.m = p.m; gp.n = p.n; gp.gscale = p.gscale;
@@ -260,8 +262,9 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
     gp.label_offset = p.label_offset; gp.negative_only = p.negative_only; gp.col_w = 0.f;
     gp.row_lse = nullptr; gp.col_lse = nullptr; gp.col_sum = nullptr; gp.bias = nullptr;
     const int nunits = u1 - u0;
-    for (int it = grp; it < nunits; it += 2) {
+    for (int it = 0; it < nunits; ++it) {
       const int u = u0 + it;
+      const int acc = it & 1;
       const int mt = u % p.tiles_m;
       const int tile = u / p.tiles_m;
       const int d = tile / p.tiles_n;
@@ -271,19 +274,19 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       gp.part_max = p.part_max[d]; gp.part_sum = p.part_sum[d]; gp.pos = p.pos[d];
       gp.c = p.c[d]; gp.scalar_acc = p.scalar_acc[d];
       const bool store_c = kStore && p.c[d] != nullptr;
-      mbar_wait(&tmem_full[grp], (it >> 1) & 1);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       EpiState st;
       epi_begin(st);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int cl = c * 32;
+      for (int c = 0; c < BN / 64; ++c) {
+        const int cl = h * (BN / 2) + c * 32;
         if (store_c && (c & 1) == 0) {
           if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
           __syncwarp();
         }
         float v[32], aux[32], o1[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + grp * BN + cl, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cl, v);
         if (n0 + cl < p.n) {
           epi_compute<EPI>(gp, row, n0 + cl, v, aux, o1, st);
           if (store_c) stage_write32(buf0, lane, c & 1, v);
@@ -300,10 +303,10 @@ gemm_peer_kernel(const __grid_constant__ PeerTmaps tm, const __grid_constant__ P
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (rank == 0) mbar_arrive(&tmem_empty[grp]);
-        else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[grp]), 0));
+        if (rank == 0) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       }
-      epi_finish<EPI>(gp, row, n0 / BN, st);  // LSE partials: one slab per column tile
+      epi_finish<EPI>(gp, row, (n0 / BN) * 2 + h, st);  // LSE partials: one slab per column half of a tile
     }
     if (kStore && lane == 0) tma_store_wait_all<0>();
   }

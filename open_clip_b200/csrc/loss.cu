@@ -74,7 +74,7 @@ extern "C" int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int3
   const int bn = peer_gemm_tile_n(world, b, e);
   if (bn == 0) return 0;
   const int64_t n = static_cast<int64_t>(world) * b;
-  const int64_t slabs = (n + bn - 1) / bn;
+  const int64_t slabs = 2 * ((n + bn - 1) / bn);  // one per column half of a tile
   return 2 * (2 * slabs * b + b);  // per direction: part_max + part_sum [slabs, b], pos [b]
 }
 
@@ -87,7 +87,7 @@ extern "C" int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, 
   CLIPN_REQUIRE(bn != 0, "clip_fwd_fused: unsupported shape (see clipn_peer_gemm_tile_n)");
   CLIPN_REQUIRE((gather_txt == nullptr) == (gather_img == nullptr), "clip_fwd_fused: both gather buffers or none");
   const int64_t n = static_cast<int64_t>(world) * b;
-  const int slabs = static_cast<int>((n + bn - 1) / bn);
+  const int slabs = 2 * static_cast<int>((n + bn - 1) / bn);
   const int64_t part = static_cast<int64_t>(slabs) * b;
   float* pos = workspace + 4 * part;  // [2, b]
   PeerGemmDesc d;
