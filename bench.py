@@ -181,8 +181,10 @@ def parity_block(model, loss_fn, image, text, rank, world, siglip):
     from oracle import clip_oracle as O
     with torch.no_grad():
         out = model(image=image, text=text)
-    fi = out["image_features"].detach().clone().requires_grad_(True)
-    ft = out["text_features"].detach().clone().requires_grad_(True)
+    # fp32 leaves holding the bf16 features' values: the loss value and the gradients come back in fp32 (a bf16 loss of
+    # ~9 carries an OUTPUT rounding of up to 0.03, more than the tolerance) while the kernels see exactly the bf16 features
+    fi = out["image_features"].detach().float().requires_grad_(True)
+    ft = out["text_features"].detach().float().requires_grad_(True)
     sc = out["logit_scale"].detach().float().clone().requires_grad_(True)
     if siglip:
         lb = out["logit_bias"].detach().float().clone().requires_grad_(True)
@@ -191,8 +193,8 @@ def parity_block(model, loss_fn, image, text, rank, world, siglip):
         loss = loss_fn(fi, ft, sc)
     loss.backward()
     if world > 1:
-        all_i = [torch.empty_like(fi) for _ in range(world)]
-        all_t = [torch.empty_like(ft) for _ in range(world)]
+        all_i = [torch.empty_like(fi.detach()) for _ in range(world)]
+        all_t = [torch.empty_like(ft.detach()) for _ in range(world)]
         dist.all_gather(all_i, fi.detach())
         dist.all_gather(all_t, ft.detach())
     else:

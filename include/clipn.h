@@ -203,16 +203,19 @@ int clipn_adamw_multi(const clipn_adamw_tensor* tensors, int32_t n, float beta1,
  * directions (logits_per_image rows, logits_per_text rows; loss.py:102-104) — and SigLipLoss (loss.py:314-489).
  *
  * FUSED FORWARD.  `txt_cols` / `img_cols` list W device pointers, each bf16 [B,E]: rank r's feature buffer,
- * peer-mapped into this process (CUDA IPC / symmetric memory) for r != rank.  ONE kernel launch streams every
- * rank's buffer tile by tile through the tensor cores over NVLink — the two all-gathers of gather_features
- * (loss.py:29-54) are fused into the logits GEMM (loss.py:102-110), every peer byte crosses NVLink once — and,
- * when gather_txt / gather_img (bf16 [N,E], local) are given, leaves the gathered operands behind for the backward.
+ * peer-mapped into this process (CUDA IPC / symmetric memory) for r != rank.  The call reads every peer's buffer
+ * directly over NVLink — no NCCL: a P2P gather kernel (coalesced 16-byte peer loads from all SMs, each byte crossing
+ * NVLink once) fills the local copies gather_txt / gather_img (bf16 [N,E], required when W > 1; the backward reads them),
+ * then ONE tcgen05 launch computes both directions with the column tile stationary in shared memory and the online
+ * log-sum-exp in the epilogue (logits never materialised):
  *   lse[0*B + m] = logsumexp_n( s * img[m] . txt_all[n] )      lse[1*B + m] = logsumexp_n( s * txt[m] . img_all[n] )
  *   loss_acc[0] += ( sum_m lse_img[m] - pos_img[m]  +  sum_m lse_txt[m] - pos_txt[m] ) / (2B)      (loss.py:135-139)
  * with s = scale * (*scale_dev) and pos = the label logit (column rank*B + m, loss.py:82-83).
- * Shapes: E % 64 == 0, E <= 1024, W <= 8, and B % 128 == 0 (B % 64 for E > 512) when W > 1;
- * clipn_peer_gemm_tile_n() returns 0 for shapes the fused kernel does not take (use the generic calls below on
- * operands gathered by the caller).  workspace: fp32, clipn_clip_fwd_fused_workspace(W, B, E) elements. */
+ * (CLIPN_PEER_DIRECT=1: the GEMM's TMA producer pulls the column tiles straight from the peers and the gathered copy is
+ * a by-product — kept for experiments; per-SM TMA peer reads are latency-bound, see csrc/loss.cu.)
+ * Shapes: E % 64 == 0, E <= 1024, W <= 8, W*B % 8 == 0; clipn_peer_gemm_tile_n(1, W*B, E) returns 0 for shapes the
+ * kernel does not take (use the generic calls below on operands gathered by the caller).
+ * workspace: fp32, clipn_clip_fwd_fused_workspace(W, B, E) elements. */
 int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e);
 int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e);
 int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,

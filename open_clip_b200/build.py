@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libclipn.so")
-SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "loss.cu", "optim.cu"]
+SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "loss.cu", "optim.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -2,15 +2,14 @@
 
 Replaces the two NCCL all-gathers of `gather_features` (reference loss.py:29-54): every rank writes its
 [B,E] bf16 image/text features into a symmetric (peer-mapped) buffer once; the fused logits kernel then reads
-every peer's buffer directly through per-rank TMA tensor maps (libclipn `txt_cols` / `img_cols`), so the gather is
-fused into the GEMM's operand loads, each peer tile crossing NVLink once, and leaves a local gathered copy behind
-as a by-product.  The backward reads only that local copy; the [N,E] gradient reduce-scatter of
+every peer's buffer directly (libclipn `txt_cols` / `img_cols`: coalesced P2P loads by all SMs, every byte crossing
+NVLink once at the fabric rate; CLIPN_PEER_DIRECT=1 instead streams TMA tiles from the peers inside the GEMM, which is
+latency-bound per SM — see csrc/loss.cu) and leaves a local gathered copy behind for the backward.  The backward reads only that local copy; the [N,E] gradient reduce-scatter of
 `_all_gather_with_grad` (loss.py:23-26) is eliminated by exchanging only the two row-LSE vectors (2*N fp32) for
 ClipLoss and nothing at all for SigLipLoss (see loss.py in this package).
 
-Envelope of the fused path: one NVLink domain with `torch.distributed._symmetric_memory`, world <= 8, per-rank batch a
-multiple of 128 (64 for embed dims above 512), embed dim a multiple of 64 and <= 1024.  Anything else — more ranks,
-several nodes, ragged batches — takes the NCCL fallback: `all_gather_into_tensor` into the same local gathered
+Envelope of the peer path: one NVLink domain with `torch.distributed._symmetric_memory`, world <= 8, embed dim a
+multiple of 64 and <= 1024.  Anything else — more ranks, several nodes — takes the NCCL fallback: `all_gather_into_tensor` into the same local gathered
 buffers, followed by the generic single-map kernels.  Same values, same gradient conventions.
 
 torch.distributed supplies the bootstrap (rendezvous + symmetric-memory handles), as in the reference
@@ -52,7 +51,7 @@ class FeatureGather:
         self.why_nccl = ""
         if os.environ.get("CLIPN_FORCE_NCCL_GATHER") == "1":
             self.why_nccl = "CLIPN_FORCE_NCCL_GATHER=1"
-        elif ops.peer_gemm_tile_n(self.world, batch, embed) == 0:
+        elif ops.peer_gemm_tile_n(1, self.world * batch, embed) == 0:
             self.why_nccl = (f"shape outside the fused kernel's envelope (world {self.world}, batch {batch}, "
                              f"embed {embed})")
         else:

@@ -96,6 +96,34 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t in
   return CLIPN_OK;
 }
 
+int make_tmap_3d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                 uint64_t stride1_bytes, uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2,
+                 int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return set_error_arg("cuTensorMapEncodeTiled entry point unavailable", __FILE__, __LINE__);
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (stride1_bytes & 15) != 0 || (stride2_bytes & 15) != 0)
+    return set_error_arg("TMA operand must be 16-byte aligned with 16-byte multiple strides", __FILE__, __LINE__);
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(out, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err),
+             "cuTensorMapEncodeTiled(3D) failed (%d): base=%p dims=%llux%llux%llu strides=%llu,%llu box=%ux%ux%u",
+             static_cast<int>(r), base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+             (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes, box0, box1, box2);
+    return CLIPN_ERR_CUDA;
+  }
+  return CLIPN_OK;
+}
+
 }  // namespace clipn
 
 extern "C" int clipn_version(void) { return 100; }

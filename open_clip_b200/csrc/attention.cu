@@ -964,11 +964,20 @@ static int pick_warps(int seq) {
 
 using namespace clipn;
 
+namespace clipn {
+// attention_tc.cu: tcgen05 / TMEM / TMA forward (default); CLIPN_ATTN_TC=0 selects the mma.sync kernels below
+bool attention_tc_enabled();
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int causal, float scale,
+                     cudaStream_t stream);
+}  // namespace clipn
+
 extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
                                    int32_t causal, float scale, clipn_stream_t stream) {
   CLIPN_REQUIRE(qkv && out, "attention_fwd: null pointer");
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_fwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
+  if (clipn::attention_tc_enabled())
+    return clipn::attention_tc_fwd(qkv, out, lse, batch, seq, heads, causal, scale, static_cast<cudaStream_t>(stream));
   const int Lp = (seq + 15) & ~15;
   const size_t stage_bytes = static_cast<size_t>(3) * Lp * LDS * 2;
   const int nst = (2 * stage_bytes <= 113 * 1024) ? 2 : 1;  // double-buffer when two CTAs still fit per SM

@@ -1,0 +1,441 @@
+// Attention core on the 5th-generation tensor cores (F.scaled_dot_product_attention, reference transformer.py:223-228),
+// forward.  tcgen05.mma with the S = Q K^T and O = P V accumulators in TMEM, operands staged by 3-D TMA boxes
+// ([column, token, sequence]: rows past the end of a sequence are zero-filled on load and clipped on store, so no
+// padding copies exist), softmax on the TMEM rows (one thread per query row, warp-shuffle-free: tcgen05.ld gives every
+// thread its whole row), P handed to the second MMA through shared memory in the canonical SW128 K-major layout.
+//
+// Tile = 128 query rows x 128 keys, head_dim 64:
+//   L <= 64   : TWO sequences share a tile (rows 0-63 / 64-127, block-diagonal mask) — ViT-B/32's 50 tokens fill 78 %
+//               of the rows instead of 39 %
+//   L <= 128  : one sequence, one key tile, softmax in one sweep (text tower: 77 tokens, causal by predicate)
+//   L  > 128  : ceil(L/128) query tiles x key tiles, TWO PASSES over the key tiles: pass 1 only takes the row maximum
+//               (S recomputed: QK^T is 1/3 of the tensor work and the tensor pipe idles behind the MUFU anyway), pass 2
+//               exponentiates against the final maximum and accumulates P V — the O accumulator in TMEM is never
+//               rescaled (ViT-L/14-336: 577 tokens = 5 x 5 tiles)
+//
+// Warp roles (384 threads, persistent, 1 CTA / SM): warp 0 TMA producer (Q tiles + a 5-stage K/V ring), warp 1 MMA
+// issuer, warp 2 TMEM allocator, warps 4-7 / 8-11 two softmax groups working on two different items: while one group
+// exponentiates, the tensor core runs the other group's QK^T / PV (FA-style ping-pong; TMEM: 2 x (128 S + 64 O) columns).
+// Producer and MMA issuer walk the same deterministic schedule (alternating one "slot" per group: [PV of the previous
+// step] + [QK^T of the next step]), so the K/V ring is consumed in exactly the order it is filled.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace clipn {
+
+constexpr int kAtThreads = 384;
+constexpr int AT_TILE = 128 * 64 * 2;  // one [128 x 64] bf16 tile, SWIZZLE_128B
+constexpr int AT_P = 128 * 128 * 2;    // P tile: two 64-wide K atoms
+constexpr int AT_STAGES = 5;
+constexpr int AT_TMEM_GROUP = 192;     // per group: S at +0 (128 columns), O at +128 (64 columns)
+constexpr int AT_SMEM = 2 * AT_TILE + 2 * AT_P + 2 * AT_TILE + AT_STAGES * AT_TILE + 256 + 1024;
+static_assert(AT_SMEM <= 227 * 1024, "attention smem budget");
+
+struct AttnFwdParams {
+  int L, B, H, D;      // tokens, sequences, heads, H * 64
+  int G, RB;           // sequences per tile (2 when L <= 64), rows per sequence in the tile (128 / G)
+  int nq, nkv, causal; // query / key tiles per sequence
+  int items;           // ceil(B / G) * H * nq
+  float scale_log2;    // softmax scale * log2(e)
+  float* lse;          // [B, H, L]
+};
+struct alignas(64) AttnMaps {
+  CUtensorMap qkv;  // [B][L][3D], box (64, RB, G)
+  CUtensorMap out;  // [B][L][D],  box (64, RB, G)
+};
+
+struct AtItem {
+  int b0, h, qt, kvn, T;
+};
+__device__ __forceinline__ AtItem at_decode(const AttnFwdParams& p, int idx) {
+  AtItem it;
+  it.qt = idx % p.nq;
+  const int r = idx / p.nq;
+  it.h = r % p.H;
+  it.b0 = (r / p.H) * p.G;
+  it.kvn = p.causal ? (it.qt + 1 < p.nkv ? it.qt + 1 : p.nkv) : p.nkv;  // causal: key tiles above the diagonal are skipped
+  it.T = it.kvn == 1 ? 1 : 2 * it.kvn;
+  return it;
+}
+__device__ __forceinline__ void at_step(const AtItem& it, int t, int& kt, bool& do_max, bool& do_exp) {
+  if (it.kvn == 1) { kt = 0; do_max = true; do_exp = true; }
+  else if (t < it.kvn) { kt = t; do_max = true; do_exp = false; }
+  else { kt = t - it.kvn; do_max = false; do_exp = true; }
+}
+
+// One group's position in the shared schedule (walked identically by the producer and the MMA issuer).
+struct AtStream {
+  int idx;           // current item
+  AtItem it;
+  int t;             // next step whose QK^T is to be issued
+  bool active;       // a QK^T remains for the current item
+  bool pv_pending;   // the PV of the last issued step is still to be issued
+  int pv_kt;
+  bool pv_first, pv_last;
+};
+__device__ __forceinline__ void at_stream_init(AtStream& s, const AttnFwdParams& p, int g) {
+  s.idx = blockIdx.x + g * gridDim.x;
+  s.active = s.idx < p.items;
+  s.pv_pending = false;
+  s.t = 0;
+  if (s.active) s.it = at_decode(p, s.idx);
+}
+// after the QK^T of step t has been issued
+__device__ __forceinline__ void at_stream_after_s(AtStream& s) {
+  int kt;
+  bool do_max, do_exp;
+  at_step(s.it, s.t, kt, do_max, do_exp);
+  const bool last = s.t == s.it.T - 1;
+  if (do_exp) {
+    s.pv_pending = true;
+    s.pv_kt = kt;
+    s.pv_first = kt == 0;
+    s.pv_last = last;
+  }
+  ++s.t;
+  if (last) s.active = false;  // until the item advances after its last PV
+}
+__device__ __forceinline__ void at_stream_after_pv(AtStream& s, const AttnFwdParams& p) {
+  s.pv_pending = false;
+  if (s.pv_last) {
+    s.idx += 2 * gridDim.x;
+    s.t = 0;
+    s.active = s.idx < p.items;
+    if (s.active) s.it = at_decode(p, s.idx);
+  }
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* q_s = smem;                       // [2] Q tile of each group
+  uint8_t* p_s = q_s + 2 * AT_TILE;          // [2] P tile of each group
+  uint8_t* o_s = p_s + 2 * AT_P;             // [2] O staging (TMA store source)
+  uint8_t* ring = o_s + 2 * AT_TILE;         // [AT_STAGES] K / V tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + AT_STAGES * AT_TILE);
+  uint64_t* q_full = bars;                   // [2]
+  uint64_t* q_empty = q_full + 2;            // [2]
+  uint64_t* kv_full = q_empty + 2;           // [AT_STAGES]
+  uint64_t* kv_empty = kv_full + AT_STAGES;  // [AT_STAGES]
+  uint64_t* s_full = kv_empty + AT_STAGES;   // [2] MMA -> softmax: S ready
+  uint64_t* s_free = s_full + 2;             // [2] softmax -> MMA: S read
+  uint64_t* p_full = s_free + 2;             // [2] softmax -> MMA: P written
+  uint64_t* pv_done = p_full + 2;            // [2] MMA -> softmax: PV retired (P reusable, O valid after the last one)
+  uint64_t* o_free = pv_done + 2;            // [2] softmax -> MMA: O read
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm.qkv);
+    tma_prefetch_desc(&tm.out);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    for (int i = 0; i < AT_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    // the P tiles start as zeros: columns a row never writes (the other sequence's block, keys past the tile) stay 0
+    const int g = (warp - 4) >> 2;
+    const int r = ((warp - 4) & 3) * 32 + lane;
+    uint4* row0 = reinterpret_cast<uint4*>(p_s + g * AT_P + r * 128);
+    uint4* row1 = reinterpret_cast<uint4*>(p_s + g * AT_P + 16384 + r * 128);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      row0[i] = make_uint4(0, 0, 0, 0);
+      row1[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== producer: Q tiles + K/V ring, in the MMA issuer's order =====================
+      AtStream st[2];
+      at_stream_init(st[0], p, 0);
+      at_stream_init(st[1], p, 1);
+      uint32_t n_q[2] = {0, 0};
+      int stage = 0;
+      uint32_t phase = 0;
+      auto ring_load = [&](const AtItem& it, int part, int kt) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], AT_TILE);
+        tma_load_3d(ring + stage * AT_TILE, &tm.qkv, &kv_full[stage], part * p.D + it.h * 64, p.G == 1 ? kt * 128 : 0, it.b0);
+        if (++stage == AT_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      while (st[0].active || st[0].pv_pending || st[1].active || st[1].pv_pending) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          AtStream& s = st[g];
+          if (s.pv_pending) {
+            ring_load(s.it, 2, s.pv_kt);  // V tile
+            at_stream_after_pv(s, p);
+          }
+          if (s.active) {
+            int kt;
+            bool dm, de;
+            at_step(s.it, s.t, kt, dm, de);
+            if (s.t == 0) {
+              if (n_q[g] > 0) mbar_wait(&q_empty[g], (n_q[g] - 1) & 1);
+              mbar_expect_tx(&q_full[g], AT_TILE);
+              tma_load_3d(q_s + g * AT_TILE, &tm.qkv, &q_full[g], s.it.h * 64, p.G == 1 ? s.it.qt * 128 : 0, s.it.b0);
+              ++n_q[g];
+            }
+            ring_load(s.it, 1, kt);  // K tile
+            at_stream_after_s(s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S[128 x 128] = Q (K-major) x K^T (K-major)
+      const uint32_t idesc_pv = umma_idesc_bf16(128, 64, 0, 1);  // O[128 x 64] += P (K-major) x V (MN-major)
+      AtStream st[2];
+      at_stream_init(st[0], p, 0);
+      at_stream_init(st[1], p, 1);
+      uint32_t n_s[2] = {0, 0}, n_p[2] = {0, 0}, n_q[2] = {0, 0}, n_o[2] = {0, 0};
+      int stage = 0;
+      uint32_t phase = 0;
+      while (st[0].active || st[0].pv_pending || st[1].active || st[1].pv_pending) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          AtStream& s = st[g];
+          const uint32_t t_s = tmem_base + g * AT_TMEM_GROUP;
+          if (s.pv_pending) {
+            mbar_wait(&p_full[g], n_p[g] & 1);
+            if (s.pv_first && n_o[g] > 0) mbar_wait(&o_free[g], (n_o[g] - 1) & 1);
+            mbar_wait(&kv_full[stage], phase);
+            tc_fence_after();
+            const int kv_valid = p.G == 2 ? 128 : (p.L - s.pv_kt * 128 < 128 ? p.L - s.pv_kt * 128 : 128);
+            const int nkk = (kv_valid + 15) >> 4;
+            const uint32_t sp = smem_u32(p_s + g * AT_P);
+            const uint32_t sv = smem_u32(ring + stage * AT_TILE);
+            for (int kk = 0; kk < nkk; ++kk)
+              umma_bf16(t_s + 128, umma_smem_desc(sp + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_smem_desc(sv + kk * 2048, 8192, 1024), idesc_pv, (s.pv_first && kk == 0) ? 0u : 1u);
+            umma_commit(&pv_done[g]);
+            umma_commit(&kv_empty[stage]);
+            if (++stage == AT_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            ++n_p[g];
+            if (s.pv_last) ++n_o[g];
+            at_stream_after_pv(s, p);
+          }
+          if (s.active) {
+            if (s.t == 0) mbar_wait(&q_full[g], n_q[g] & 1);
+            if (n_s[g] > 0) mbar_wait(&s_free[g], (n_s[g] - 1) & 1);
+            mbar_wait(&kv_full[stage], phase);
+            tc_fence_after();
+            const uint32_t sq = smem_u32(q_s + g * AT_TILE);
+            const uint32_t sk = smem_u32(ring + stage * AT_TILE);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(t_s, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024), idesc_s,
+                        k > 0 ? 1u : 0u);
+            umma_commit(&s_full[g]);
+            umma_commit(&kv_empty[stage]);
+            if (++stage == AT_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            if (s.t == s.it.T - 1) {
+              umma_commit(&q_empty[g]);  // the item's last QK^T: its Q tile may be replaced
+              ++n_q[g];
+            }
+            ++n_s[g];
+            at_stream_after_s(s);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax groups: one thread per query row =====================
+    const int g = (warp - 4) >> 2;
+    const int quarter = (warp - 4) & 3;
+    const int r = quarter * 32 + lane;
+    const bool leader = quarter == 0 && lane == 0;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + g * AT_TMEM_GROUP;
+    uint8_t* pbuf = p_s + g * AT_P;
+    uint8_t* obuf = o_s + g * AT_TILE;
+    uint32_t n_s = 0, n_p = 0;
+    for (int idx = blockIdx.x + g * gridDim.x; idx < p.items; idx += 2 * gridDim.x) {
+      const AtItem it = at_decode(p, idx);
+      const int seq = p.G == 2 ? (r >> 6) : 0;
+      const int qi = p.G == 2 ? (r & 63) : it.qt * 128 + r;
+      const int b = it.b0 + seq;
+      const int cbase = seq * 64;  // this row's key block inside the tile (G == 2: block-diagonal)
+      float m = -INFINITY, l = 0.f;
+      for (int t = 0; t < it.T; ++t) {
+        int kt;
+        bool do_max, do_exp;
+        at_step(it, t, kt, do_max, do_exp);
+        const int kv0 = p.G == 2 ? 0 : kt * 128;
+        const int kv_valid = p.G == 2 ? p.L : (p.L - kv0 < 128 ? p.L - kv0 : 128);
+        int kmax = kv_valid;  // keys [0, kmax) of the block are visible to this row
+        if (p.causal) {
+          const int c = qi - kv0 + 1;
+          kmax = c < kmax ? c : kmax;
+          kmax = kmax < 1 ? 1 : kmax;  // rows past the sequence end are never stored; keep them finite
+        }
+        const int nchunk = (kv_valid + 31) >> 5;  // warp-uniform
+        mbar_wait(&s_full[g], n_s & 1);
+        tc_fence_after();
+        if (do_max) {
+          for (int j = 0; j < nchunk; ++j) {
+            float v[32];
+            tmem_ld_32x32(t_row + cbase + j * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, (j * 32 + i < kmax) ? v[i] * p.scale_log2 : -INFINITY);
+          }
+        }
+        if (do_exp) {
+          if (n_p > 0) mbar_wait(&pv_done[g], (n_p - 1) & 1);  // the previous PV has finished reading the P tile
+          for (int j = 0; j < nchunk; ++j) {
+            float v[32];
+            tmem_ld_32x32(t_row + cbase + j * 32, v);
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              v[i] = (j * 32 + i < kmax) ? ex2_approx(fmaf(v[i], p.scale_log2, -m)) : 0.f;
+              v[i + 1] = (j * 32 + i + 1 < kmax) ? ex2_approx(fmaf(v[i + 1], p.scale_log2, -m)) : 0.f;
+              s0 += v[i];
+              s1 += v[i + 1];
+            }
+            l += s0 + s1;
+            const int c0 = cbase + j * 32;  // first column of this chunk inside the P tile
+            uint8_t* rowp = pbuf + (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float t8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) t8[i] = v[q4 * 8 + i];
+              const int ch = ((c0 & 63) >> 3) + q4;
+              *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = pack_bf16x8(t8);
+            }
+          }
+          fence_proxy_async_smem();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_free[g]);
+          if (do_exp) mbar_arrive(&p_full[g]);
+        }
+        ++n_s;
+        if (do_exp) ++n_p;
+      }
+      // ---- O epilogue: O / l -> bf16 -> swizzled staging tile -> one TMA store (rows past L / B are clipped)
+      mbar_wait(&pv_done[g], (n_p - 1) & 1);
+      tc_fence_after();
+      if (leader) tma_store_wait_read<0>();  // the previous item's store has read the staging tile
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float v[32];
+        tmem_ld_32x32(t_row + 128 + j * 32, v);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = v[q4 * 8 + i] * inv;
+          const int ch = j * 4 + q4;
+          *reinterpret_cast<uint4*>(obuf + r * 128 + ((ch ^ (r & 7)) << 4)) = pack_bf16x8(t8);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[g]);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+      if (leader) {
+        tma_store_3d(&tm.out, obuf, it.h * 64, p.G == 1 ? it.qt * 128 : 0, it.b0);
+        tma_store_commit();
+      }
+      if (qi < p.L && b < p.B)
+        p.lse[(static_cast<int64_t>(b) * p.H + it.h) * p.L + qi] = (m + lg2_approx(l)) * 0.69314718055994531f;
+    }
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------
+bool attention_tc_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPN_ATTN_TC");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
+
+int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int causal, float scale,
+                     cudaStream_t stream) {
+  int cc_major = 0, sms = 0, cc_minor = 0;
+  clipn_device_info(&sms, &cc_major, &cc_minor);
+  CLIPN_REQUIRE(cc_major == 10, "attention: the tcgen05 kernels require an sm_100 (B200) device");
+  CLIPN_REQUIRE(lse != nullptr, "attention_fwd: lse buffer required");
+  AttnFwdParams p;
+  p.L = seq; p.B = batch; p.H = heads; p.D = heads * 64;
+  p.G = seq <= 64 ? 2 : 1;
+  p.RB = 128 / p.G;
+  p.nq = p.G == 2 ? 1 : (seq + 127) / 128;
+  p.nkv = p.nq;
+  p.causal = causal ? 1 : 0;
+  p.items = ((batch + p.G - 1) / p.G) * heads * p.nq;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
+  AttnMaps tm;
+  const uint64_t d3 = static_cast<uint64_t>(3) * p.D, d1 = static_cast<uint64_t>(p.D);
+  int rc = make_tmap_3d(&tm.qkv, qkv, 2, d3, seq, batch, d3 * 2, d3 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tm.out, out, 2, d1, seq, batch, d1 * 2, d1 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    configured = true;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  attention_tc_fwd_kernel<<<grid, kAtThreads, AT_SMEM, stream>>>(tm, p);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+}  // namespace clipn

@@ -7,6 +7,7 @@
 // gathered operands behind.  Backward: d(logits) tiles are recomputed from the LSE vectors against the LOCAL
 // gathered copy (generic kernel, one tensor map), written once in bf16 and contracted by a split-K GEMM.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -52,6 +53,78 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Peer gather: every rank's [B, E] bf16 feature block -> this rank's local [W*B, E] copies, by plain 16-byte loads from
+// the peer-mapped buffers (NVLink / NVSwitch P2P) with 8 independent loads in flight per thread x 2048 threads per SM.
+// Why not TMA tiles straight into the GEMM (CLIPN_PEER_DIRECT=1 keeps that path): a TMA box over a peer tensor is
+// fetched as one 128-byte NVLink read per row with few requests outstanding — measured on 2 x B200, a CTA refilling
+// its 128 KB column tile on demand waited ~140 us (0.9 GB/s per SM), while all SMs pulling coalesced 16-byte loads
+// together run at the fabric rate.  So the operand crosses NVLink exactly once, at full rate, and the GEMM that
+// follows reads L2-resident local memory.
+// ---------------------------------------------------------------------------------------------------------------------
+struct GatherPtrs {
+  const uint4* src[2][kMaxBMaps];  // [direction][rank]
+  uint4* dst[2];
+  int world;
+  int64_t block16;                 // 16-byte elements per rank block (B * E * 2 / 16)
+};
+
+__global__ void __launch_bounds__(512) peer_gather_kernel(const __grid_constant__ GatherPtrs g) {
+  constexpr int U = 8;
+  const int64_t per_dir = g.block16 * g.world;
+  const int64_t total = 2 * per_dir;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int dir = i >= per_dir;
+        const int64_t j = i - dir * per_dir;
+        const int r = static_cast<int>(j / g.block16);
+        v[u] = __ldg(g.src[dir][r] + (j - r * g.block16));  // peer addresses bypass the local L2 anyway
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int dir = i >= per_dir;
+        g.dst[dir][i - dir * per_dir] = v[u];
+      }
+    }
+  }
+}
+
+static bool peer_direct() {
+  static const bool on = [] {
+    const char* e = getenv("CLIPN_PEER_DIRECT");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+// gather every rank's columns into the local copies; afterwards the GEMM sees ONE local [W*B, E] operand per direction
+static int gather_columns(const void* const* txt_cols, const void* const* img_cols, int world, int b, int e, void* gather_txt,
+                          void* gather_img, cudaStream_t stream) {
+  CLIPN_REQUIRE(gather_txt != nullptr && gather_img != nullptr, "fused forward: world > 1 needs the local gather buffers");
+  CLIPN_REQUIRE((static_cast<int64_t>(b) * e * 2) % 16 == 0, "fused forward: B * E must be a multiple of 8");
+  GatherPtrs g;
+  for (int r = 0; r < world; ++r) {
+    CLIPN_REQUIRE(txt_cols[r] != nullptr && img_cols[r] != nullptr, "fused forward: null column pointer");
+    g.src[0][r] = reinterpret_cast<const uint4*>(txt_cols[r]);
+    g.src[1][r] = reinterpret_cast<const uint4*>(img_cols[r]);
+  }
+  g.dst[0] = reinterpret_cast<uint4*>(gather_txt);
+  g.dst[1] = reinterpret_cast<uint4*>(gather_img);
+  g.world = world;
+  g.block16 = static_cast<int64_t>(b) * e * 2 / 16;
+  peer_gather_kernel<<<num_sms() * 4, 512, 0, stream>>>(g);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
 static void base_desc(clipn_gemm_desc& d, const void* rows, const void* cols, int m, int n, int e, float scale,
                       const float* scale_dev) {
   memset(&d, 0, sizeof(d));
@@ -71,7 +144,7 @@ using namespace clipn;
 extern "C" int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e) { return peer_gemm_tile_n(world, b, e); }
 
 extern "C" int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e) {
-  const int bn = peer_gemm_tile_n(world, b, e);
+  const int bn = (world > 1 && peer_direct()) ? peer_gemm_tile_n(world, b, e) : peer_gemm_tile_n(1, world * b, e);
   if (bn == 0) return 0;
   const int64_t n = static_cast<int64_t>(world) * b;
   const int64_t slabs = 2 * ((n + bn - 1) / bn);  // one per column half of a tile
@@ -83,18 +156,31 @@ extern "C" int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, 
                                     float scale, const float* scale_dev, void* gather_txt, void* gather_img, float* lse,
                                     float* loss_acc, float* workspace, clipn_stream_t stream) {
   CLIPN_REQUIRE(img_rows && txt_rows && txt_cols && img_cols && lse && workspace, "clip_fwd_fused: null pointer");
-  const int bn = peer_gemm_tile_n(world, b, e);
-  CLIPN_REQUIRE(bn != 0, "clip_fwd_fused: unsupported shape (see clipn_peer_gemm_tile_n)");
+  CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "clip_fwd_fused: world must be 1..8");
   CLIPN_REQUIRE((gather_txt == nullptr) == (gather_img == nullptr), "clip_fwd_fused: both gather buffers or none");
+  const bool direct = world > 1 && peer_direct();  // TMA tiles straight from the peers inside the GEMM (experiment)
+  const int bn = direct ? peer_gemm_tile_n(world, b, e) : peer_gemm_tile_n(1, world * b, e);
+  CLIPN_REQUIRE(bn != 0, "clip_fwd_fused: unsupported shape (see clipn_peer_gemm_tile_n)");
   const int64_t n = static_cast<int64_t>(world) * b;
   const int slabs = 2 * static_cast<int>((n + bn - 1) / bn);
   const int64_t part = static_cast<int64_t>(slabs) * b;
   float* pos = workspace + 4 * part;  // [2, b]
+  const void* local_txt[1] = {gather_txt};
+  const void* local_img[1] = {gather_img};
   PeerGemmDesc d;
   memset(&d, 0, sizeof(d));
-  d.rows[0] = img_rows; d.cols[0] = txt_cols; d.gather[0] = gather_txt;
-  d.rows[1] = txt_rows; d.cols[1] = img_cols; d.gather[1] = gather_img;
-  d.dirs = 2; d.world = world; d.rank = rank; d.m = b; d.rows_per_map = b; d.e = e;
+  d.rows[0] = img_rows; d.rows[1] = txt_rows;
+  d.dirs = 2; d.m = b; d.e = e;
+  if (world > 1 && !direct) {
+    int rcg = gather_columns(txt_cols, img_cols, world, b, e, gather_txt, gather_img, static_cast<cudaStream_t>(stream));
+    if (rcg) return rcg;
+    d.cols[0] = local_txt; d.cols[1] = local_img;
+    d.world = 1; d.rank = 0; d.rows_per_map = static_cast<int>(n);
+  } else {
+    d.cols[0] = txt_cols; d.cols[1] = img_cols;
+    d.gather[0] = gather_txt; d.gather[1] = gather_img;
+    d.world = world; d.rank = rank; d.rows_per_map = b;
+  }
   d.epilogue = CLIPN_EPI_LSE;
   d.alpha = scale; d.alpha_dev = scale_dev;
   d.label_offset = world > 1 ? rank * b : 0;
@@ -119,13 +205,27 @@ extern "C" int clipn_siglip_fwd_fused(const void* img_rows, const void* txt_rows
                                       int64_t ld, clipn_stream_t stream) {
   CLIPN_REQUIRE(img_rows && txt_rows && txt_cols && img_cols && loss_acc && scale_dev, "siglip_fwd_fused: null pointer");
   CLIPN_REQUIRE((dl_img == nullptr) == (dl_txt == nullptr), "siglip_fwd_fused: both d(logits) buffers or none");
+  CLIPN_REQUIRE(world >= 1 && world <= kMaxBMaps, "siglip_fwd_fused: world must be 1..8");
   const int dirs = dl_txt != nullptr ? 2 : 1;  // the text direction only produces gradients
+  const bool direct = world > 1 && peer_direct();
+  const int64_t n = static_cast<int64_t>(world) * b;
+  const void* local_txt[1] = {gather_txt};
+  const void* local_img[1] = {gather_img};
   PeerGemmDesc d;
   memset(&d, 0, sizeof(d));
-  d.rows[0] = img_rows; d.cols[0] = txt_cols; d.gather[0] = gather_txt;
-  d.rows[1] = txt_rows; d.cols[1] = img_cols; d.gather[1] = dirs == 2 ? gather_img : nullptr;
-  if (dirs == 1) d.gather[0] = nullptr;        // nothing downstream reads the gathered copy without a backward
-  d.dirs = dirs; d.world = world; d.rank = rank; d.m = b; d.rows_per_map = b; d.e = e;
+  d.rows[0] = img_rows; d.rows[1] = txt_rows;
+  d.dirs = dirs; d.m = b; d.e = e;
+  if (world > 1 && !direct) {
+    int rcg = gather_columns(txt_cols, img_cols, world, b, e, gather_txt, gather_img, static_cast<cudaStream_t>(stream));
+    if (rcg) return rcg;
+    d.cols[0] = local_txt; d.cols[1] = local_img;
+    d.world = 1; d.rank = 0; d.rows_per_map = static_cast<int>(n);
+  } else {
+    d.cols[0] = txt_cols; d.cols[1] = img_cols;
+    d.gather[0] = dirs == 2 ? gather_txt : nullptr;  // nothing downstream reads the copies without a backward
+    d.gather[1] = dirs == 2 ? gather_img : nullptr;
+    d.world = world; d.rank = rank; d.rows_per_map = b;
+  }
   d.epilogue = CLIPN_EPI_SIGLIP;
   d.alpha = 1.0f; d.alpha_dev = scale_dev; d.logit_bias = 0.f; d.logit_bias_dev = bias_dev;
   d.gscale = gscale;

@@ -309,7 +309,7 @@ def clip_fwd_fused(img: torch.Tensor, txt: torch.Tensor, txt_ptrs: Sequence[int]
         _call(L.lib().clipn_clip_fwd_fused(img.data_ptr(), txt.data_ptr(), _ptr_array(txt_ptrs), _ptr_array(img_ptrs),
                                              world, rank, b, e, 1.0, scale.data_ptr(), _ptr(gather_txt),
                                              _ptr(gather_img), lse.data_ptr(), loss.data_ptr(), ws.data_ptr(),
-                                             _stream()), 2)
+                                             _stream()), 2 + int(world > 1))
     return lse, loss
 
 
@@ -326,9 +326,9 @@ def siglip_fwd_fused(img, txt, txt_ptrs, img_ptrs, rank, scale, bias, gscale, ga
     with _profiled(((2 if want_grad else 1) * b, n, e, L.EPI_SIGLIP, False, False)):
         _call(L.lib().clipn_siglip_fwd_fused(img.data_ptr(), txt.data_ptr(), _ptr_array(txt_ptrs), _ptr_array(img_ptrs),
                                                world, rank, b, e, scale.data_ptr(), bias.data_ptr(), gscale,
-                                               _ptr(gather_txt) if want_grad else None,
-                                               _ptr(gather_img) if want_grad else None, loss_acc.data_ptr(),
-                                               _ptr(scalar_acc), _ptr(dl_i), _ptr(dl_t), ld, _stream()))
+                                               _ptr(gather_txt), _ptr(gather_img), loss_acc.data_ptr(),
+                                               _ptr(scalar_acc), _ptr(dl_i), _ptr(dl_t), ld, _stream()),
+              1 + int(world > 1))
     return dl_i, dl_t
 
 

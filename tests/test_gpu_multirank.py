@@ -17,7 +17,8 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SHAPES = [(256, 512), (1024, 512), (256, 64), (128, 768)]  # (per-rank batch, embed dim); 768 = ViT-L/14 (BN = 64 tiles)
+# (per-rank batch, embed dim); 768 = ViT-L/14 (128-wide column tiles); 200 = a batch that is no multiple of the tile
+SHAPES = [(256, 512), (1024, 512), (256, 64), (128, 768), (200, 512)]
 
 
 def _rel(a, b):
@@ -35,8 +36,10 @@ def _check_shape(rank, world, B, E, modes_seen):
     fi, ft = [t.float() for t in img], [t.float() for t in txt]
     for local_loss in (True, False):
         for gwg in (True, False):
-            gi = img[rank].cuda().clone().requires_grad_(True)
-            gt = txt[rank].cuda().clone().requires_grad_(True)
+            # fp32 leaves holding bf16-representable values: the loss comes back in fp32 (a bf16 loss of ~9 carries an
+            # output rounding of up to 0.03) while the kernels see exactly the bf16 features
+            gi = img[rank].float().cuda().requires_grad_(True)
+            gt = txt[rank].float().cuda().requires_grad_(True)
             gs = scale.cuda().clone().requires_grad_(True)
             mod = NativeClipLoss(local_loss=local_loss, gather_with_grad=gwg, rank=rank, world_size=world)
             loss = mod(gi, gt, gs)
@@ -51,8 +54,8 @@ def _check_shape(rank, world, B, E, modes_seen):
             assert abs(float(gs.grad) - float(d_scale)) < 2e-2 * abs(float(d_scale)) + 1e-5, (tag, "d_scale")
     # SigLIP (all dist_impl's are the same sum; ours reads peer blocks in place, no reverse exchange)
     bias = torch.tensor(-10.0)
-    gi = img[rank].cuda().clone().requires_grad_(True)
-    gt = txt[rank].cuda().clone().requires_grad_(True)
+    gi = img[rank].float().cuda().requires_grad_(True)
+    gt = txt[rank].float().cuda().requires_grad_(True)
     gs, gb = torch.tensor(10.0).cuda().requires_grad_(True), bias.cuda().clone().requires_grad_(True)
     loss = NativeSigLipLoss(rank=rank, world_size=world)(gi, gt, gs, gb)
     loss.backward()
