@@ -117,10 +117,12 @@ int clipn_gemm_tile_n(int n);
 /* ---- LayerNorm (layers.py:11-26, eps 1e-5; fp32 statistics, bf16 in/out) --------------------- */
 int clipn_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                         int64_t rows, int32_t d, float eps, clipn_stream_t stream);
-/* dx_out = (dx_resid ? dx_resid : 0) + LN'(dy); dgamma/dbeta are fp32 accumulators (+=). */
+/* dx_out = (dx_resid ? dx_resid : 0) + LN'(dy); dgamma/dbeta are fp32 accumulators (+=).
+ * dresid_sum (optional, fp32 [d], +=): column sums of dx_resid — the bias gradient of the Linear that fed the residual
+ * stream (out_proj.bias / c_proj.bias, transformer.py:328-329), fused into the pass that streams dx_resid anyway. */
 int clipn_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
-                        const void* dx_resid, void* dx_out, float* dgamma, float* dbeta, int64_t rows, int32_t d,
-                        clipn_stream_t stream);
+                        const void* dx_resid, void* dx_out, float* dgamma, float* dbeta, float* dresid_sum, int64_t rows,
+                        int32_t d, clipn_stream_t stream);
 
 /* ---- attention core (F.scaled_dot_product_attention, transformer.py:223-228) ------------------
  * qkv: bf16 [B*L, 3*H*64] (q | k | v, head-major inside each third, as produced by the QKV GEMM);
@@ -217,6 +219,9 @@ int clipn_adamw_multi(const clipn_adamw_tensor* tensors, int32_t n, float beta1,
  * kernel does not take (use the generic calls below on operands gathered by the caller).
  * workspace: fp32, clipn_clip_fwd_fused_workspace(W, B, E) elements. */
 int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e);
+/* The gather step alone: every rank's [B,E] block (peer-mapped pointers) -> local gather_txt / gather_img [W*B,E]. */
+int clipn_peer_gather(const void* const* txt_cols, const void* const* img_cols, int32_t world, int32_t b, int32_t e,
+                      void* gather_txt, void* gather_img, clipn_stream_t stream);
 int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e);
 int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
                          const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e, float scale,

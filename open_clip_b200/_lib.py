@@ -55,7 +55,7 @@ SIGNATURES = {
     "clipn_gemm_ref": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "clipn_gemm_tile_n": (C.c_int, [C.c_int]),
     "clipn_layernorm_fwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _F, _P]),
-    "clipn_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "clipn_layernorm_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "clipn_attention_fwd": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "clipn_attention_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P]),
     "clipn_patchify": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
@@ -73,6 +73,7 @@ SIGNATURES = {
     "clipn_cast_f32_to_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "clipn_adamw_multi": (C.c_int, [C.POINTER(AdamTensor), _I32, _F, _F, _F, _F, _F, _P]),
     "clipn_peer_gemm_tile_n": (_I32, [_I32, _I32, _I32]),
+    "clipn_peer_gather": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _P, _P, _P]),
     "clipn_clip_fwd_fused_workspace": (C.c_int64, [_I32, _I32, _I32]),
     "clipn_clip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32, _F,
                                        _P, _P, _P, _P, _P, _P, _P]),

@@ -969,6 +969,8 @@ namespace clipn {
 bool attention_tc_enabled();
 int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int seq, int heads, int causal, float scale,
                      cudaStream_t stream);
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
+                     int batch, int seq, int heads, int causal, float scale, cudaStream_t stream);
 }  // namespace clipn
 
 extern "C" int clipn_attention_fwd(const void* qkv, void* out, float* lse, int32_t batch, int32_t seq, int32_t heads,
@@ -1025,6 +1027,9 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   CLIPN_REQUIRE(qkv && dout && lse && dqkv, "attention_bwd: null pointer");
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_bwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
+  if (clipn::attention_tc_enabled() && seq <= 128 && out != nullptr)
+    return clipn::attention_tc_bwd(qkv, out, dout, lse, dqkv, dbias, batch, seq, heads, causal, scale,
+                                   static_cast<cudaStream_t>(stream));
   const int Lp = (seq + 15) & ~15;
   const int nw = pick_warps(seq);
   static const bool small_enabled = [] {

@@ -28,7 +28,8 @@ constexpr int kAtThreads = 384;
 constexpr int AT_TILE = 128 * 64 * 2;  // one [128 x 64] bf16 tile, SWIZZLE_128B
 constexpr int AT_P = 128 * 128 * 2;    // P tile: two 64-wide K atoms
 constexpr int AT_STAGES = 5;
-constexpr int AT_TMEM_GROUP = 192;     // per group: S at +0 (128 columns), O at +128 (64 columns)
+constexpr int AT_TMEM_GROUP = 192;
+constexpr float kLog2eAt = 1.4426950408889634f;     // per group: S at +0 (128 columns), O at +128 (64 columns)
 constexpr int AT_SMEM = 2 * AT_TILE + 2 * AT_P + 2 * AT_TILE + AT_STAGES * AT_TILE + 256 + 1024;
 static_assert(AT_SMEM <= 227 * 1024, "attention smem budget");
 
@@ -394,6 +395,290 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ===================================================================================================
+// Backward, sequences of at most 128 tokens (both CLIP ViT-B towers: 50 / 77; ViT-L text: 77) — one tile per item,
+// everything in one pass:
+//   S = Q K^T, dP = dO V^T               (TMEM, 2 x 128 columns)
+//   P = exp(S - lse), dS = P o (dP - D) * scale, D = rowsum(dO o O)      (8 warps: TMEM lane quarter x column half)
+//   dV = P^T dO, dK = dS^T Q, dQ = dS K  (TMEM, 3 x 64 columns)
+// P and dS are written once to shared memory in the SW128 layout that is at the same time the K-major operand
+// [q][key] (dQ = dS K) and the MN-major operand [key][q]^T (dV = P^T dO, dK = dS^T Q): no transposition anywhere.
+// Likewise every input tile [rows x 64] serves as K-major operand (contraction over head_dim) and MN-major operand
+// (contraction over rows) in its natural TMA layout.  Outputs leave through the input stage's own tiles (dQ over Q,
+// dK over K, dV over V) by three TMA stores; the in_proj bias gradient (column sums of dqkv) is accumulated per head
+// in shared memory and flushed with one atomicAdd per column when the CTA's contiguous item range changes head.
+// ===================================================================================================
+constexpr int AT_BWD_SMEM = 2 * 4 * AT_TILE + 2 * AT_P + 192 * 4 + 256 + 1024;
+static_assert(AT_BWD_SMEM <= 227 * 1024, "attention bwd smem budget");
+
+struct AttnBwdParams {
+  int L, B, H, D, G, RB, causal;
+  int items, nb;       // nb = ceil(B / G); item idx = h * nb + bi
+  float scale, scale_log2;
+  const float* lse;    // [B, H, L]
+  const __nv_bfloat16* out;  // [B*L, D]
+  float* dbias;        // [3D] or null
+};
+struct alignas(64) AttnBwdMaps {
+  CUtensorMap qkv;   // [B][L][3D] loads
+  CUtensorMap dout;  // [B][L][D]  loads
+  CUtensorMap dqkv;  // [B][L][3D] stores
+};
+
+// lane l receives the sum over the warp's 32 rows of column l (v is destroyed) — see epi_col_sum in gemm.cu
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* in_s = smem;                     // [2 stages][Q, K, V, dO]
+  uint8_t* p_s = in_s + 2 * 4 * AT_TILE;    // P tile
+  uint8_t* ds_s = p_s + AT_P;               // dS tile
+  float* bias_s = reinterpret_cast<float*>(ds_s + AT_P);  // [3][64] per-head bias-gradient accumulators
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 192);
+  uint64_t* in_full = bars;       // [2]
+  uint64_t* in_empty = bars + 2;  // [2]
+  uint64_t* sdp_full = bars + 4;  // S and dP in TMEM
+  uint64_t* pds_full = bars + 5;  // P and dS in shared memory (8 warps)
+  uint64_t* out_full = bars + 6;  // dV, dK, dQ in TMEM
+  uint64_t* acc_free = bars + 7;  // TMEM read by the epilogue (8 warps)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // contiguous item range of this CTA (items are head-major: a CTA sees at most a couple of heads)
+  const int i0 = static_cast<int>((static_cast<int64_t>(p.items) * blockIdx.x) / gridDim.x);
+  const int i1 = static_cast<int>((static_cast<int64_t>(p.items) * (blockIdx.x + 1)) / gridDim.x);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm.qkv);
+    tma_prefetch_desc(&tm.dout);
+    tma_prefetch_desc(&tm.dqkv);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&in_full[i], 1);
+      mbar_init(&in_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(out_full, 1);
+    mbar_init(acc_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    // P / dS start as zeros and are never used as staging: the off-diagonal blocks (two sequences per tile) and
+    // the key columns no row writes stay zero for the whole kernel
+    const int t = threadIdx.x - 128;  // 0..255
+    uint4* z = reinterpret_cast<uint4*>(p_s);
+    for (int i = t; i < 2 * AT_P / 16; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    if (t < 192) bias_s[t] = 0.f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int nk = p.G == 2 ? 8 : (p.L + 15) >> 4;  // contraction steps over rows (queries or keys): 16 rows each
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== producer =====================
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, stage = n & 1;
+        const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
+        if (n >= 2) mbar_wait(&in_empty[stage], ((n >> 1) - 1) & 1);
+        uint8_t* st = in_s + stage * 4 * AT_TILE;
+        mbar_expect_tx(&in_full[stage], 4 * AT_TILE);
+        tma_load_3d(st, &tm.qkv, &in_full[stage], h * 64, 0, b0);
+        tma_load_3d(st + AT_TILE, &tm.qkv, &in_full[stage], p.D + h * 64, 0, b0);
+        tma_load_3d(st + 2 * AT_TILE, &tm.qkv, &in_full[stage], 2 * p.D + h * 64, 0, b0);
+        tma_load_3d(st + 3 * AT_TILE, &tm.dout, &in_full[stage], h * 64, 0, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);   // [128 x 128] = A (K-major) x B (K-major), K = head_dim
+      const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);    // [keys x 64] = A^T (MN-major) x B (MN-major), K = queries
+      const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);    // [queries x 64] = A (K-major) x B (MN-major), K = keys
+      const uint32_t sp = smem_u32(p_s), sds = smem_u32(ds_s);
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, stage = n & 1;
+        const uint32_t sq = smem_u32(in_s + stage * 4 * AT_TILE), sk = sq + AT_TILE, sv = sq + 2 * AT_TILE, sdo = sq + 3 * AT_TILE;
+        mbar_wait(&in_full[stage], (n >> 1) & 1);
+        if (n > 0) mbar_wait(acc_free, (n - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base + 128, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), id_s,
+                    k > 0);
+        umma_commit(sdp_full);
+        mbar_wait(pds_full, n & 1);
+        tc_fence_after();
+        for (int kk = 0; kk < nk; ++kk)  // dV[key, d] = sum_q P[q, key] dO[q, d]
+          umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, 16384, 1024), umma_smem_desc(sdo + kk * 2048, 8192, 1024),
+                    id_t, kk > 0);
+        for (int kk = 0; kk < nk; ++kk)  // dK[key, d] = sum_q dS[q, key] Q[q, d]
+          umma_bf16(tmem_base + 320, umma_smem_desc(sds + kk * 2048, 16384, 1024), umma_smem_desc(sq + kk * 2048, 8192, 1024),
+                    id_t, kk > 0);
+        for (int kk = 0; kk < nk; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]
+          umma_bf16(tmem_base + 384, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                    umma_smem_desc(sk + kk * 2048, 8192, 1024), id_q, kk > 0);
+        umma_commit(out_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax-gradient + epilogue warps: (TMEM lane quarter, column half) =====================
+    const int quarter = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    const bool leader = warp == 4 && lane == 0;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int cur_h = -1;
+    auto flush_bias = [&]() {  // all 256 threads
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - 128;
+      if (t < 192 && p.dbias != nullptr && cur_h >= 0) {
+        atomicAdd(p.dbias + (t >> 6) * p.D + cur_h * 64 + (t & 63), bias_s[t]);
+        bias_s[t] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    for (int idx = i0; idx < i1; ++idx) {
+      const int n = idx - i0, stage = n & 1;
+      const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
+      if (h != cur_h) {
+        if (cur_h >= 0) flush_bias();
+        cur_h = h;
+      }
+      uint8_t* st = in_s + stage * 4 * AT_TILE;
+      const int seq = p.G == 2 ? (r >> 6) : 0;
+      const int qi = p.G == 2 ? (r & 63) : r;
+      const int b = b0 + seq;
+      const bool valid = qi < p.L && b < p.B;
+      const int cbase = seq * 64;
+      int kmax = p.L;
+      if (p.causal) kmax = qi + 1 < kmax ? qi + 1 : kmax;
+      // D = rowsum(dO o O): dO row from the staged tile, O row from global memory (128 contiguous bytes)
+      mbar_wait(&in_full[stage], (n >> 1) & 1);
+      float lse2 = 0.f, drow = 0.f;
+      if (valid) {
+        lse2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt;
+        const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.L + qi) * p.D + h * 64);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a[8], d8[8];
+          unpack_bf16x8(__ldg(orow + c), a);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 3 * AT_TILE + r * 128 + ((c ^ (r & 7)) << 4)), d8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) drow = fmaf(a[i], d8[i], drow);
+        }
+      }
+      mbar_wait(sdp_full, n & 1);
+      tc_fence_after();
+      const int nchunk = p.G == 2 ? 2 : (p.L + 31) >> 5;   // 32-column chunks holding keys of this row's block
+      const int per = p.G == 2 ? 1 : 2;                    // chunks per column half
+      for (int jj = 0; jj < per; ++jj) {
+        const int j = half * per + jj;
+        if (j >= nchunk) break;
+        float s[32], dp[32];
+        tmem_ld_32x32(t_row + cbase + j * 32, s);
+        tmem_ld_32x32(t_row + 128 + cbase + j * 32, dp);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const bool ok = valid && (j * 32 + i < kmax);
+          const float pr = ok ? ex2_approx(fmaf(s[i], p.scale_log2, -lse2)) : 0.f;
+          s[i] = pr;
+          dp[i] = pr * (dp[i] - drow) * p.scale;
+        }
+        const int c0 = cbase + j * 32;
+        const int off = (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float t8[8], u8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            t8[i] = s[q4 * 8 + i];
+            u8[i] = dp[q4 * 8 + i];
+          }
+          const int ch = ((((c0 & 63) >> 3) + q4) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(p_s + off + ch) = pack_bf16x8(t8);
+          *reinterpret_cast<uint4*>(ds_s + off + ch) = pack_bf16x8(u8);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      // ---- epilogue: dV | dK | dQ columns [half*32, half*32+32) of row r -> bf16 -> the stage's V | K | Q tile
+      mbar_wait(out_full, n & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int part = 0; part < 3; ++part) {  // part 0: dQ (TMEM 384, over Q), 1: dK (320, over K), 2: dV (256, over V)
+        float v[32];
+        tmem_ld_32x32(t_row + 384 - part * 64 + half * 32, v);
+        uint8_t* dst = st + part * AT_TILE + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = v[q4 * 8 + i];
+          const uint4 pk = pack_bf16x8(t8);
+          *reinterpret_cast<uint4*>(dst + (((half * 4 + q4) ^ (r & 7)) << 4)) = pk;
+          unpack_bf16x8(pk, t8);  // the bias gradient sums the ROUNDED values (== column sums of the stored dqkv)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[q4 * 8 + i] = t8[i];
+        }
+        if (p.dbias != nullptr) {
+          const float cs = warp_transpose_sum(v);
+          atomicAdd(bias_s + part * 64 + half * 32 + lane, cs);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (leader) {
+        tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
+        tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
+        tma_store_3d(&tm.dqkv, st + 2 * AT_TILE, 2 * p.D + h * 64, 0, b0);
+        tma_store_commit();
+        tma_store_wait_read<0>();       // the stage's tiles have been read: the producer may refill them
+        mbar_arrive(&in_empty[stage]);
+      }
+    }
+    if (cur_h >= 0) flush_bias();
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
@@ -434,6 +719,40 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int seq,
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
   attention_tc_fwd_kernel<<<grid, kAtThreads, AT_SMEM, stream>>>(tm, p);
+  CLIPN_CHECK_CUDA(cudaGetLastError());
+  return CLIPN_OK;
+}
+
+int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
+                     int batch, int seq, int heads, int causal, float scale, cudaStream_t stream) {
+  CLIPN_REQUIRE(seq <= 128, "attention_tc_bwd: single-tile kernel (L <= 128)");
+  CLIPN_REQUIRE(out != nullptr, "attention_bwd: the forward output is required (D = rowsum(dO o O))");
+  AttnBwdParams p;
+  p.L = seq; p.B = batch; p.H = heads; p.D = heads * 64;
+  p.G = seq <= 64 ? 2 : 1;
+  p.RB = 128 / p.G;
+  p.causal = causal ? 1 : 0;
+  p.nb = (batch + p.G - 1) / p.G;
+  p.items = p.nb * heads;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
+  p.out = reinterpret_cast<const __nv_bfloat16*>(out);
+  p.dbias = dbias;
+  AttnBwdMaps tm;
+  const uint64_t d3 = static_cast<uint64_t>(3) * p.D, d1 = static_cast<uint64_t>(p.D);
+  int rc = make_tmap_3d(&tm.qkv, qkv, 2, d3, seq, batch, d3 * 2, d3 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tm.dout, dout, 2, d1, seq, batch, d1 * 2, d1 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tm.dqkv, dqkv, 2, d3, seq, batch, d3 * 2, d3 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  static bool configured = false;
+  if (!configured) {
+    CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_BWD_SMEM));
+    configured = true;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  attention_tc_bwd_kernel<<<grid, kAtThreads, AT_BWD_SMEM, stream>>>(tm, p);
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;
 }

@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 4 : 3) layernorm_fwd_kernel(
 // LayerNorm backward.  dx = rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*gamma; dgamma += sum dy*xhat,
 // dbeta += sum dy.  Optional residual-gradient add fused into the store.
 // ------------------------------------------------------------------------------------------------
-template <int NCH>
+// kRSum: also accumulate the column sums of the residual gradient (dresid_sum[d] += sum_rows dx_resid) — that is the
+// bias gradient of the Linear whose output the residual stream received (out_proj / c_proj, transformer.py:328-329), so
+// the two stand-alone column-sum launches per block disappear into the pass that already streams dx_resid.
+template <int NCH, bool kRSum>
 __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                             const __nv_bfloat16* __restrict__ x,
                                                             const float* __restrict__ mean_in,
@@ -107,20 +110,28 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
                                                             const float* __restrict__ gamma,
                                                             const __nv_bfloat16* __restrict__ dx_resid,
                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int64_t rows, int d) {
-  extern __shared__ float sred[];  // [2][d]
+                                                            float* __restrict__ dbeta, float* __restrict__ dresid_sum,
+                                                            int64_t rows, int d) {
+  extern __shared__ float sred[];  // [2 or 3][d]
   float* s_dg = sred;
   float* s_db = sred + d;
-  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) sred[i] = 0.f;
+  float* s_dr = sred + 2 * d;
+  for (int i = threadIdx.x; i < (kRSum ? 3 : 2) * d; i += blockDim.x) sred[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nchunk = d >> 3;
-  float acc_dg[NCH][8], acc_db[NCH][8];
+  float acc_dg[NCH][8], acc_db[NCH][8], acc_dr[kRSum ? NCH : 1][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_dg[c][j] = acc_db[c][j] = 0.f;
+  if (kRSum) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc_dr[c][j] = 0.f;
+  }
 
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < rows;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
@@ -177,6 +188,10 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (dv[j] * gm[j] - s1 - (xv[j] - mean) * rstd * s2) + r[j];
         dxr[ci] = pack_bf16x8(o);
+        if (kRSum) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_dr[c][j] += r[j];
+        }
       }
     }
   }
@@ -189,6 +204,7 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
       for (int j = 0; j < 8; ++j) {
         atomicAdd(&s_dg[ci * 8 + j], acc_dg[c][j]);
         atomicAdd(&s_db[ci * 8 + j], acc_db[c][j]);
+        if (kRSum) atomicAdd(&s_dr[ci * 8 + j], acc_dr[c][j]);
       }
     }
   }
@@ -196,6 +212,7 @@ __global__ void __launch_bounds__(256, (NCH <= 2) ? 3 : 2) layernorm_bwd_kernel(
   for (int i = threadIdx.x; i < d; i += blockDim.x) {
     if (dgamma) atomicAdd(&dgamma[i], s_dg[i]);
     if (dbeta) atomicAdd(&dbeta[i], s_db[i]);
+    if (kRSum) atomicAdd(&dresid_sum[i], s_dr[i]);
   }
 }
 
@@ -569,17 +586,21 @@ extern "C" int clipn_layernorm_fwd(const void* x, const float* gamma, const floa
 
 extern "C" int clipn_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                                    const float* gamma, const void* dx_resid, void* dx_out, float* dgamma, float* dbeta,
-                                   int64_t rows, int32_t d, clipn_stream_t stream) {
+                                   float* dresid_sum, int64_t rows, int32_t d, clipn_stream_t stream) {
   CLIPN_REQUIRE(dy && x && mean && rstd && gamma && dx_out, "layernorm_bwd: null pointer");
+  CLIPN_REQUIRE(dresid_sum == nullptr || dx_resid != nullptr, "layernorm_bwd: dresid_sum needs dx_resid");
   CLIPN_REQUIRE(d % 8 == 0 && d <= 1024 && d > 0, "layernorm: d must be a multiple of 8 and <= 1024");
   if (rows <= 0) return CLIPN_OK;
   int64_t blocks = (rows + 7) / 8;
   const int cap = num_sms() * (d <= 512 ? 3 : 2);  // one resident wave: every block does a single dgamma/dbeta flush
   const int grid = static_cast<int>(blocks < cap ? blocks : cap);
-#define CLIPN_LN_BWD(N)                                                                                              \
-  layernorm_bwd_kernel<N><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(BF(dy), BF(x), mean, rstd, gamma,          \
-                                                                             BF(dx_resid), BFW(dx_out), dgamma, dbeta, \
-                                                                             rows, d)
+#define CLIPN_LN_BWD(N)                                                                                                 \
+  if (dresid_sum != nullptr)                                                                                            \
+    layernorm_bwd_kernel<N, true><<<grid, 256, 3 * d * sizeof(float), ST(stream)>>>(                                     \
+        BF(dy), BF(x), mean, rstd, gamma, BF(dx_resid), BFW(dx_out), dgamma, dbeta, dresid_sum, rows, d);                \
+  else                                                                                                                  \
+    layernorm_bwd_kernel<N, false><<<grid, 256, 2 * d * sizeof(float), ST(stream)>>>(                                    \
+        BF(dy), BF(x), mean, rstd, gamma, BF(dx_resid), BFW(dx_out), dgamma, dbeta, nullptr, rows, d)
   CLIPN_DISPATCH_NCH(d, CLIPN_LN_BWD);
 #undef CLIPN_LN_BWD
   CLIPN_CHECK_CUDA(cudaGetLastError());

@@ -125,6 +125,15 @@ static int gather_columns(const void* const* txt_cols, const void* const* img_co
   return CLIPN_OK;
 }
 
+}  // namespace clipn
+extern "C" int clipn_peer_gather(const void* const* txt_cols, const void* const* img_cols, int32_t world, int32_t b,
+                                 int32_t e, void* gather_txt, void* gather_img, clipn_stream_t stream) {
+  CLIPN_REQUIRE(txt_cols && img_cols, "peer_gather: null pointer");
+  CLIPN_REQUIRE(world >= 1 && world <= clipn::kMaxBMaps, "peer_gather: world must be 1..8");
+  return clipn::gather_columns(txt_cols, img_cols, world, b, e, gather_txt, gather_img, static_cast<cudaStream_t>(stream));
+}
+namespace clipn {
+
 static void base_desc(clipn_gemm_desc& d, const void* rows, const void* cols, int m, int n, int e, float scale,
                       const float* scale_dev) {
   memset(&d, 0, sizeof(d));

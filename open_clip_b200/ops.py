@@ -121,12 +121,16 @@ def layernorm_fwd(x, gamma, beta, out=None, eps: float = 1e-5, save_stats: bool 
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=None, out=None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, resid=None, out=None, resid_sum=None):
+    """resid_sum (fp32 [d], +=): column sums of `resid` = bias gradient of the Linear that fed the residual stream."""
     _chk(dy, BF16, "lnb.dy"); _chk(x, BF16, "lnb.x")
     rows, d = x.shape
     dx = out if out is not None else torch.empty_like(x)
+    if resid_sum is not None:
+        _chk(resid_sum, F32, "lnb.resid_sum")
     _call(L.lib().clipn_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
-                                        _ptr(resid), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, d, _stream()))
+                                        _ptr(resid), dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), _ptr(resid_sum), rows, d,
+                                        _stream()))
     return dx
 
 
@@ -274,6 +278,13 @@ def _ptr_array(ptrs: Sequence[int]):
 def peer_gemm_tile_n(world: int, b: int, e: int) -> int:
     """Column-tile width of the fused peer-streaming forward for this shape, 0 if it does not take it."""
     return int(L.lib().clipn_peer_gemm_tile_n(world, b, e))
+
+
+def peer_gather(txt_ptrs: Sequence[int], img_ptrs: Sequence[int], b: int, e: int, gather_txt: torch.Tensor,
+                gather_img: torch.Tensor):
+    """The P2P gather step alone (every rank's [B,E] block -> local [W*B,E] copies)."""
+    _call(L.lib().clipn_peer_gather(_ptr_array(txt_ptrs), _ptr_array(img_ptrs), len(txt_ptrs), b, e,
+                                     gather_txt.data_ptr(), gather_img.data_ptr(), _stream()))
 
 
 def _profiled(sig):

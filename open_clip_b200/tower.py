@@ -178,7 +178,6 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
         ops.gemm(dx_out, P[pre + ".mlp.c_proj.weight"], b_mn=True, epilogue=L.EPI_DGELU, aux=s.h_pre, out=dh, out2=g,
                  col_sum=G[pre + ".mlp.c_fc.bias"])
     _wgrad(dx_out, g, G[pre + ".mlp.c_proj.weight"])
-    ops.colsum(dx_out, G[pre + ".mlp.c_proj.bias"])
     if s.h2 is not None:
         h2 = s.h2
     else:
@@ -188,13 +187,13 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     dh2 = ws.get("dh_small", (M, d), BF16, dev)
     ops.gemm(dh, P[pre + ".mlp.c_fc.weight"], b_mn=True, out=dh2)
     dx_mid = ws.get("dx_mid", (M, d), BF16, dev)
+    # ln_2 backward streams dx_out as the residual gradient: the c_proj bias gradient (its column sums) rides along
     ops.layernorm_bwd(dh2, s.x_mid, s.ln2_mean, s.ln2_rstd, P[pre + ".ln_2.weight"], G[pre + ".ln_2.weight"],
-                      G[pre + ".ln_2.bias"], resid=dx_out, out=dx_mid)
+                      G[pre + ".ln_2.bias"], resid=dx_out, out=dx_mid, resid_sum=G[pre + ".mlp.c_proj.bias"])
     # ---- attention
     datt = ws.get("dh_small", (M, d), BF16, dev)
     ops.gemm(dx_mid, P[pre + ".attn.out_proj.weight"], b_mn=True, out=datt)
     _wgrad(dx_mid, s.att, G[pre + ".attn.out_proj.weight"])
-    ops.colsum(dx_mid, G[pre + ".attn.out_proj.bias"])
     dqkv = ws.get("dqkv", (M, 3 * d), BF16, dev)
     ops.attention_bwd(s.qkv, s.att, datt, s.lse, batch, cfg.seq, cfg.heads, cfg.causal, out=dqkv,
                       dbias=G[pre + ".attn.in_proj_bias"])
@@ -207,8 +206,9 @@ def block_backward(P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor], pre: 
     dh1 = ws.get("dh_small", (M, d), BF16, dev)
     ops.gemm(dqkv, P[pre + ".attn.in_proj_weight"], b_mn=True, out=dh1)
     dx_in = torch.empty((M, d), dtype=BF16, device=dev)
+    # ln_1 backward streams dx_mid: the out_proj bias gradient rides along
     ops.layernorm_bwd(dh1, s.x_in, s.ln1_mean, s.ln1_rstd, P[pre + ".ln_1.weight"], G[pre + ".ln_1.weight"],
-                      G[pre + ".ln_1.bias"], resid=dx_mid, out=dx_in)
+                      G[pre + ".ln_1.bias"], resid=dx_mid, out=dx_in, resid_sum=G[pre + ".attn.out_proj.bias"])
     return dx_in
 
 

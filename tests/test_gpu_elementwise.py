@@ -29,6 +29,12 @@ def test_layernorm_fwd_bwd(rows, d):
     assert rel_err(dx, xr.grad + resid.float()) < 5e-3
     assert rel_err(dg, gr.grad) < 1e-3
     assert rel_err(db, br.grad) < 1e-3
+    # fused bias gradient of the Linear that fed the residual stream: column sums of the residual gradient (+=)
+    rs = torch.ones(d, dtype=F32, device="cuda")
+    dg2, db2 = torch.zeros_like(dg), torch.zeros_like(db)
+    dx2 = ops.layernorm_bwd(dy, x, mean, rstd, gamma, dg2, db2, resid=resid, resid_sum=rs)
+    assert torch.equal(dx2, dx) and rel_err(dg2, dg) < 1e-5
+    assert rel_err(rs, 1.0 + resid.float().sum(0)) < 1e-4
 
 
 def test_patchify_matches_conv_unfold():

@@ -3,7 +3,7 @@ benchmarked embed dim (E = 512) and per-rank batches 256 and 1024: the peer-memo
 against (a) the oracle's process-group-free restatement of the reference's multi-rank semantics — itself pinned to
 real gloo runs of the reference by oracle/gen_golden.py and tests/test_oracle.py — for all four
 (local_loss, gather_with_grad) modes, and (b) the committed gloo fixtures tests/golden/loss_w{2,4,8}.pt (reference
-outputs; B = 8, E = 64, which also exercises the NCCL-gather fallback path for shapes outside the fused envelope).
+outputs; B = 8, E = 64, through the peer path and through the forced NCCL-gather fallback).
 Tolerances (bf16 features, fp32 LSE, d(logits) rounded to bf16 once): loss 1e-2 abs, feature grads 1.5e-2 rel-L2,
 logit_scale / logit_bias grads 2e-2 rel."""
 import os
@@ -69,30 +69,34 @@ def _check_shape(rank, world, B, E, modes_seen):
 
 
 def _check_golden(rank, world):
-    """The committed outputs of the REAL reference under gloo (fp32 features, B = 8, E = 64): fallback path."""
+    """The committed outputs of the REAL reference under gloo (fp32 features, B = 8, E = 64), through both exchange
+    modes: the peer path and the NCCL all-gather fallback (what runs across nodes / without symmetric memory)."""
     from open_clip_b200.loss import NativeClipLoss, NativeSigLipLoss
     gold = torch.load(os.path.join(GOLDEN, f"loss_w{world}.pt"), weights_only=False)
     f = gold["feats"]
-    for case in gold["cases"]:
-        want = case["ranks"][rank]
-        gi = f["img"][rank].cuda().clone().requires_grad_(True)   # fp32 features in, bf16 inside
-        gt = f["txt"][rank].cuda().clone().requires_grad_(True)
-        gs = f["scale"].cuda().clone().requires_grad_(True)
-        if case["kind"] == "clip":
-            mod = NativeClipLoss(rank=rank, world_size=world, **case["kwargs"])
-            loss = mod(gi, gt, gs)
-        else:
-            gb = f["bias"].cuda().clone().requires_grad_(True)
-            mod = NativeSigLipLoss(rank=rank, world_size=world, **case["kwargs"])
-            loss = mod(gi, gt, gs, gb)
-        loss.backward()
-        torch.cuda.synchronize()
-        assert mod.exchange_mode == "nccl", mod.exchange_mode  # B = 8 is outside the fused kernel's envelope
-        tag = (world, case["kind"], case["kwargs"], rank)
-        assert abs(float(loss) - want["loss"]) < 2e-2 + 1e-2 * abs(want["loss"]), (tag, float(loss), want["loss"])
-        assert _rel(gi.grad, want["d_img"]) < 2e-2, (tag, "d_img", _rel(gi.grad, want["d_img"]))
-        assert _rel(gt.grad, want["d_txt"]) < 2e-2, (tag, "d_txt", _rel(gt.grad, want["d_txt"]))
-        assert abs(float(gs.grad) - want["d_scale"]) < 3e-2 * abs(want["d_scale"]) + 1e-4, (tag, "d_scale")
+    for force_nccl in (False, True):
+        os.environ["CLIPN_FORCE_NCCL_GATHER"] = "1" if force_nccl else "0"
+        for case in gold["cases"]:
+            want = case["ranks"][rank]
+            gi = f["img"][rank].cuda().clone().requires_grad_(True)   # fp32 features in, bf16 inside
+            gt = f["txt"][rank].cuda().clone().requires_grad_(True)
+            gs = f["scale"].cuda().clone().requires_grad_(True)
+            if case["kind"] == "clip":
+                mod = NativeClipLoss(rank=rank, world_size=world, **case["kwargs"])
+                loss = mod(gi, gt, gs)
+            else:
+                gb = f["bias"].cuda().clone().requires_grad_(True)
+                mod = NativeSigLipLoss(rank=rank, world_size=world, **case["kwargs"])
+                loss = mod(gi, gt, gs, gb)
+            loss.backward()
+            torch.cuda.synchronize()
+            assert mod.exchange_mode == ("nccl" if force_nccl else "peer"), mod.exchange_mode
+            tag = (world, case["kind"], case["kwargs"], rank, mod.exchange_mode)
+            assert abs(float(loss) - want["loss"]) < 2e-2 + 1e-2 * abs(want["loss"]), (tag, float(loss), want["loss"])
+            assert _rel(gi.grad, want["d_img"]) < 2e-2, (tag, "d_img", _rel(gi.grad, want["d_img"]))
+            assert _rel(gt.grad, want["d_txt"]) < 2e-2, (tag, "d_txt", _rel(gt.grad, want["d_txt"]))
+            assert abs(float(gs.grad) - want["d_scale"]) < 3e-2 * abs(want["d_scale"]) + 1e-4, (tag, "d_scale")
+    os.environ["CLIPN_FORCE_NCCL_GATHER"] = "0"
 
 
 def _worker(rank, world, port):

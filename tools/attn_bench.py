@@ -1,9 +1,11 @@
 """Time the attention kernels alone: python tools/attn_bench.py B L H [causal] [B L H causal ...]  (CUDA events)."""
+import os
 import sys
 
 import torch
 
-from open_clip_b200 import ops
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from open_clip_b200 import ops  # noqa: E402
 
 
 def main():
