@@ -206,6 +206,9 @@ def text_embed_fwd(ids, table, pos):
     _chk(ids, torch.int64, "temb.ids"); _chk(table, F32, "temb.table"); _chk(pos, F32, "temb.pos")
     B, S = ids.shape
     vocab, d = table.shape
+    # nn.Embedding raises on an out-of-range id (tokenizer / vocab mismatch); the kernel would clamp it silently, so the
+    # range is asserted on the device (asynchronously: no host sync, a violation surfaces as a CUDA device assert)
+    torch._assert_async(((ids >= 0) & (ids < vocab)).all(), "open_clip_b200: token id outside [0, vocab_size)")
     x = torch.empty((B * S, d), dtype=BF16, device=ids.device)
     eot = torch.empty(B, dtype=torch.int32, device=ids.device)
     _call(L.lib().clipn_text_embed_fwd(ids.data_ptr(), table.data_ptr(), pos.data_ptr(), x.data_ptr(), eot.data_ptr(),
