@@ -1027,7 +1027,7 @@ extern "C" int clipn_attention_bwd(const void* qkv, const void* out, const void*
   CLIPN_REQUIRE(qkv && dout && lse && dqkv, "attention_bwd: null pointer");
   CLIPN_REQUIRE(seq > 0 && heads > 0, "attention_bwd: bad dims");
   if (batch <= 0) return CLIPN_OK;
-  if (clipn::attention_tc_enabled() && seq <= 128 && out != nullptr)
+  if (clipn::attention_tc_enabled() && out != nullptr)
     return clipn::attention_tc_bwd(qkv, out, dout, lse, dqkv, dbias, batch, seq, heads, causal, scale,
                                    static_cast<cudaStream_t>(stream));
   const int Lp = (seq + 15) & ~15;

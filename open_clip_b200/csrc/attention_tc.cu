@@ -679,6 +679,327 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ===================================================================================================
+// Backward, sequences longer than 128 tokens (ViT-B/16: 197, ViT-L/14-336: 577): two launches of one kernel.
+//   kDKDV : item = (sequence, head, KEY tile j): K_j, V_j stay in shared memory, the query tiles i stream past
+//           them; dV_j += P_ij^T dO_i and dK_j += dS_ij^T Q_i accumulate in TMEM over i and are stored once
+//   kDQ   : item = (sequence, head, QUERY tile i): Q_i, dO_i stay, the key tiles stream; dQ_i += dS_ij K_j
+// S and dP are recomputed in both launches (4 of the 7-9 MMAs per tile pair: the tensor pipe waits for the MUFU
+// anyway) so that no gradient is ever accumulated through global memory.  Same P / dS shared-memory tiles, same
+// operand-layout reuse and the same 8-warp softmax-gradient stage as the single-tile kernel above.
+// ===================================================================================================
+constexpr int AT_BWDL_SMEM = 2 * 2 * AT_TILE + 2 * 2 * AT_TILE + 2 * AT_P + 192 * 4 + 256 + 1024;
+static_assert(AT_BWDL_SMEM <= 227 * 1024, "attention bwd (long) smem budget");
+
+struct AttnBwdLongParams {
+  int L, B, H, D, nt, causal;  // nt = ceil(L / 128) tiles per sequence
+  int items;                   // B * H * nt, item idx = (h * B + b) * nt + s  (head-major: few heads per CTA)
+  float scale, scale_log2;
+  const float* lse;
+  const __nv_bfloat16* out;
+  float* dbias;
+};
+
+template <bool kDKDV>
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc_bwd_long_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_constant__ AttnBwdLongParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stat_base = smem;                 // [2 items] stationary pair: kDKDV ? (K_j, V_j) : (Q_i, dO_i)
+  uint8_t* str_s = stat_base + 2 * 2 * AT_TILE;  // [2 stages] streamed pair: kDKDV ? (Q_i, dO_i) : (K_j, V_j)
+  uint8_t* p_s = str_s + 2 * 2 * AT_TILE;    // P tile
+  uint8_t* ds_s = p_s + AT_P;                // dS tile
+  float* bias_s = reinterpret_cast<float*>(ds_s + AT_P);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 192);
+  uint64_t* stat_full = bars;      // [2] stationary pair of item n & 1 landed
+  uint64_t* stat_empty = bars + 2; // [2] its tiles (and the output staging over them) have been read
+  uint64_t* str_full = bars + 4;   // [2]
+  uint64_t* str_empty = bars + 6;  // [2]
+  uint64_t* sdp_full = bars + 8;
+  uint64_t* pds_full = bars + 9;   // 8 warps
+  uint64_t* out_full = bars + 10;
+  uint64_t* acc_free = bars + 11;  // 8 warps
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int i0 = static_cast<int>((static_cast<int64_t>(p.items) * blockIdx.x) / gridDim.x);
+  const int i1 = static_cast<int>((static_cast<int64_t>(p.items) * (blockIdx.x + 1)) / gridDim.x);
+  // inner range of an item with stationary tile s: the other side's tiles [t_lo, t_hi)
+  auto inner = [&](int s, int& t_lo, int& t_hi) {
+    if (kDKDV) { t_lo = p.causal ? s : 0; t_hi = p.nt; }       // query tiles that see key tile s
+    else { t_lo = 0; t_hi = p.causal ? s + 1 : p.nt; }         // key tiles visible to query tile s
+  };
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm.qkv);
+    tma_prefetch_desc(&tm.dout);
+    tma_prefetch_desc(&tm.dqkv);
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stat_full[i], 1);
+      mbar_init(&stat_empty[i], 1);
+      mbar_init(&str_full[i], 1);
+      mbar_init(&str_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(out_full, 1);
+    mbar_init(acc_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  if (warp >= 4) {
+    const int t = threadIdx.x - 128;
+    uint4* z = reinterpret_cast<uint4*>(p_s);
+    for (int i = t; i < 2 * AT_P / 16; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    if (t < 192) bias_s[t] = 0.f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ===================== producer =====================
+      uint32_t n_str = 0;
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, slot = n & 1;
+        const int s = idx % p.nt, b = (idx / p.nt) % p.B, h = idx / (p.nt * p.B);
+        uint8_t* stat_s = stat_base + slot * 2 * AT_TILE;
+        if (n >= 2) mbar_wait(&stat_empty[slot], ((n >> 1) - 1) & 1);
+        mbar_expect_tx(&stat_full[slot], 2 * AT_TILE);
+        if (kDKDV) {
+          tma_load_3d(stat_s, &tm.qkv, &stat_full[slot], p.D + h * 64, s * 128, b);               // K_s
+          tma_load_3d(stat_s + AT_TILE, &tm.qkv, &stat_full[slot], 2 * p.D + h * 64, s * 128, b);  // V_s
+        } else {
+          tma_load_3d(stat_s, &tm.qkv, &stat_full[slot], h * 64, s * 128, b);                      // Q_s
+          tma_load_3d(stat_s + AT_TILE, &tm.dout, &stat_full[slot], h * 64, s * 128, b);           // dO_s
+        }
+        int t_lo, t_hi;
+        inner(s, t_lo, t_hi);
+        for (int t = t_lo; t < t_hi; ++t, ++n_str) {
+          const int stage = n_str & 1;
+          if (n_str >= 2) mbar_wait(&str_empty[stage], ((n_str >> 1) - 1) & 1);
+          uint8_t* st = str_s + stage * 2 * AT_TILE;
+          mbar_expect_tx(&str_full[stage], 2 * AT_TILE);
+          if (kDKDV) {
+            tma_load_3d(st, &tm.qkv, &str_full[stage], h * 64, t * 128, b);                 // Q_t
+            tma_load_3d(st + AT_TILE, &tm.dout, &str_full[stage], h * 64, t * 128, b);      // dO_t
+          } else {
+            tma_load_3d(st, &tm.qkv, &str_full[stage], p.D + h * 64, t * 128, b);           // K_t
+            tma_load_3d(st + AT_TILE, &tm.qkv, &str_full[stage], 2 * p.D + h * 64, t * 128, b);  // V_t
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ===================== MMA issuer =====================
+      const uint32_t id_s = umma_idesc_bf16(128, 128, 0, 0);
+      const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);
+      const uint32_t sp = smem_u32(p_s), sds = smem_u32(ds_s);
+      uint32_t n_str = 0;
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, slot = n & 1;
+        const int s = idx % p.nt;
+        const uint32_t s0 = smem_u32(stat_base + slot * 2 * AT_TILE), s1 = s0 + AT_TILE;
+        int t_lo, t_hi;
+        inner(s, t_lo, t_hi);
+        mbar_wait(&stat_full[slot], (n >> 1) & 1);
+        if (n > 0) mbar_wait(acc_free, (n - 1) & 1);
+        for (int t = t_lo; t < t_hi; ++t, ++n_str) {
+          const int stage = n_str & 1;
+          const uint32_t r0 = smem_u32(str_s + stage * 2 * AT_TILE), r1 = r0 + AT_TILE;
+          // operand roles: Q / dO tiles index queries, K / V tiles index keys
+          const uint32_t sq = kDKDV ? r0 : s0, sdo = kDKDV ? r1 : s1, sk = kDKDV ? s0 : r0, sv = kDKDV ? s1 : r1;
+          const int qt = kDKDV ? t : s, kt = kDKDV ? s : t;
+          mbar_wait(&str_full[stage], (n_str >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, umma_smem_desc(sq + k * 32, 16, 1024), umma_smem_desc(sk + k * 32, 16, 1024), id_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + 128, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), id_s,
+                      k > 0);
+          umma_commit(sdp_full);
+          mbar_wait(pds_full, n_str & 1);
+          tc_fence_after();
+          const int q_valid = p.L - qt * 128 < 128 ? p.L - qt * 128 : 128;
+          const int k_valid = p.L - kt * 128 < 128 ? p.L - kt * 128 : 128;
+          const uint32_t acc = (t > t_lo) ? 1u : 0u;
+          if (kDKDV) {
+            const int nk = (q_valid + 15) >> 4;  // contraction over the queries of tile t
+            for (int kk = 0; kk < nk; ++kk)
+              umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, 16384, 1024),
+                        umma_smem_desc(sdo + kk * 2048, 8192, 1024), id_t, (kk > 0) ? 1u : acc);
+            for (int kk = 0; kk < nk; ++kk)
+              umma_bf16(tmem_base + 320, umma_smem_desc(sds + kk * 2048, 16384, 1024),
+                        umma_smem_desc(sq + kk * 2048, 8192, 1024), id_t, (kk > 0) ? 1u : acc);
+          } else {
+            const int nk = (k_valid + 15) >> 4;  // contraction over the keys of tile t
+            for (int kk = 0; kk < nk; ++kk)
+              umma_bf16(tmem_base + 256, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_smem_desc(sk + kk * 2048, 8192, 1024), id_q, (kk > 0) ? 1u : acc);
+          }
+          umma_commit(&str_empty[stage]);
+        }
+        umma_commit(out_full);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax-gradient + epilogue warps =====================
+    const int quarter = (warp - 4) & 3, half = (warp - 4) >> 2;
+    const int r = quarter * 32 + lane;
+    const bool leader = warp == 4 && lane == 0;
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    int cur_h = -1;
+    uint32_t n_str = 0;
+    auto flush_bias = [&]() {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int t = threadIdx.x - 128;
+      if (t < 192 && p.dbias != nullptr && cur_h >= 0) {
+        atomicAdd(p.dbias + (t >> 6) * p.D + cur_h * 64 + (t & 63), bias_s[t]);
+        bias_s[t] = 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    for (int idx = i0; idx < i1; ++idx) {
+      const int n = idx - i0, slot = n & 1;
+      const int s = idx % p.nt, b = (idx / p.nt) % p.B, h = idx / (p.nt * p.B);
+      uint8_t* stat_s = stat_base + slot * 2 * AT_TILE;
+      if (h != cur_h) {
+        if (cur_h >= 0) flush_bias();
+        cur_h = h;
+      }
+      int t_lo, t_hi;
+      inner(s, t_lo, t_hi);
+      mbar_wait(&stat_full[slot], (n >> 1) & 1);
+      for (int t = t_lo; t < t_hi; ++t, ++n_str) {
+        const int stage = n_str & 1;
+        const int qt = kDKDV ? t : s, kt = kDKDV ? s : t;
+        const uint8_t* do_tile = kDKDV ? str_s + stage * 2 * AT_TILE + AT_TILE : stat_s + AT_TILE;
+        const int qi = qt * 128 + r;
+        const bool valid = qi < p.L;
+        const int kv0 = kt * 128;
+        const int k_valid = p.L - kv0 < 128 ? p.L - kv0 : 128;
+        int kmax = k_valid;
+        if (p.causal) {
+          const int c = qi - kv0 + 1;
+          kmax = c < kmax ? c : kmax;
+        }
+        mbar_wait(&str_full[stage], (n_str >> 1) & 1);
+        float lse2 = 0.f, drow = 0.f;
+        if (valid) {
+          lse2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt;
+          const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.L + qi) * p.D + h * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float a[8], d8[8];
+            unpack_bf16x8(__ldg(orow + c), a);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(do_tile + r * 128 + ((c ^ (r & 7)) << 4)), d8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) drow = fmaf(a[i], d8[i], drow);
+          }
+        }
+        mbar_wait(sdp_full, n_str & 1);
+        tc_fence_after();
+        const int nchunk = (k_valid + 31) >> 5;
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = half * 2 + jj;
+          if (j >= nchunk) break;
+          float sv[32], dp[32];
+          tmem_ld_32x32(t_row + j * 32, sv);
+          tmem_ld_32x32(t_row + 128 + j * 32, dp);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = valid && (j * 32 + i < kmax);
+            const float pr = ok ? ex2_approx(fmaf(sv[i], p.scale_log2, -lse2)) : 0.f;
+            sv[i] = pr;
+            dp[i] = pr * (dp[i] - drow) * p.scale;
+          }
+          const int c0 = j * 32;
+          const int off = (c0 >> 6) * 16384 + r * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float t8[8], u8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              t8[i] = sv[q4 * 8 + i];
+              u8[i] = dp[q4 * 8 + i];
+            }
+            const int ch = ((((c0 & 63) >> 3) + q4) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(p_s + off + ch) = pack_bf16x8(t8);
+            *reinterpret_cast<uint4*>(ds_s + off + ch) = pack_bf16x8(u8);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+      }
+      // ---- item epilogue: accumulators -> bf16 -> the stationary pair's tiles -> TMA store
+      mbar_wait(out_full, n & 1);
+      tc_fence_after();
+      constexpr int kParts = kDKDV ? 2 : 1;
+#pragma unroll 1
+      for (int pi = 0; pi < kParts; ++pi) {
+        // kDKDV: pi 0 = dV (TMEM 256) staged over V (stat tile 1), pi 1 = dK (TMEM 320) over K (stat tile 0); kDQ: dQ over Q
+        const int part = kDKDV ? (pi == 0 ? 2 : 1) : 0;  // column third of dqkv: 0 q, 1 k, 2 v
+        float v[32];
+        tmem_ld_32x32(t_row + 256 + pi * 64 + half * 32, v);
+        uint8_t* dst = stat_s + (kDKDV ? (pi == 0 ? AT_TILE : 0) : 0) + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = v[q4 * 8 + i];
+          const uint4 pk = pack_bf16x8(t8);
+          *reinterpret_cast<uint4*>(dst + (((half * 4 + q4) ^ (r & 7)) << 4)) = pk;
+          unpack_bf16x8(pk, t8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[q4 * 8 + i] = (s * 128 + r < p.L) ? t8[i] : 0.f;  // rows past L are clipped by the store
+        }
+        if (p.dbias != nullptr) {
+          const float cs = warp_transpose_sum(v);
+          atomicAdd(bias_s + part * 64 + half * 32 + lane, cs);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_free);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (leader) {
+        if (kDKDV) {
+          tma_store_3d(&tm.dqkv, stat_s, p.D + h * 64, s * 128, b);                 // dK_s
+          tma_store_3d(&tm.dqkv, stat_s + AT_TILE, 2 * p.D + h * 64, s * 128, b);   // dV_s
+        } else {
+          tma_store_3d(&tm.dqkv, stat_s, h * 64, s * 128, b);                       // dQ_s
+        }
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&stat_empty[slot]);
+      }
+    }
+    if (cur_h >= 0) flush_bias();
+    if (leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
@@ -725,8 +1046,40 @@ int attention_tc_fwd(const void* qkv, void* out, float* lse, int batch, int seq,
 
 int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dbias,
                      int batch, int seq, int heads, int causal, float scale, cudaStream_t stream) {
-  CLIPN_REQUIRE(seq <= 128, "attention_tc_bwd: single-tile kernel (L <= 128)");
   CLIPN_REQUIRE(out != nullptr, "attention_bwd: the forward output is required (D = rowsum(dO o O))");
+  if (seq > 128) {
+    AttnBwdLongParams q;
+    q.L = seq; q.B = batch; q.H = heads; q.D = heads * 64;
+    q.nt = (seq + 127) / 128;
+    q.causal = causal ? 1 : 0;
+    q.items = batch * heads * q.nt;
+    q.scale = scale; q.scale_log2 = scale * 1.4426950408889634f;
+    q.lse = lse;
+    q.out = reinterpret_cast<const __nv_bfloat16*>(out);
+    q.dbias = dbias;
+    AttnBwdMaps tl;
+    const uint64_t e3 = static_cast<uint64_t>(3) * q.D, e1 = static_cast<uint64_t>(q.D);
+    int rl = make_tmap_3d(&tl.qkv, qkv, 2, e3, seq, batch, e3 * 2, e3 * 2 * seq, 64, 128, 1, 128);
+    if (rl) return rl;
+    rl = make_tmap_3d(&tl.dout, dout, 2, e1, seq, batch, e1 * 2, e1 * 2 * seq, 64, 128, 1, 128);
+    if (rl) return rl;
+    rl = make_tmap_3d(&tl.dqkv, dqkv, 2, e3, seq, batch, e3 * 2, e3 * 2 * seq, 64, 128, 1, 128);
+    if (rl) return rl;
+    static bool configured_long = false;
+    if (!configured_long) {
+      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_bwd_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            AT_BWDL_SMEM));
+      CLIPN_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_bwd_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            AT_BWDL_SMEM));
+      configured_long = true;
+    }
+    const int gl = q.items < num_sms() ? q.items : num_sms();
+    attention_tc_bwd_long_kernel<true><<<gl, kAtThreads, AT_BWDL_SMEM, stream>>>(tl, q);   // dK, dV
+    CLIPN_CHECK_CUDA(cudaGetLastError());
+    attention_tc_bwd_long_kernel<false><<<gl, kAtThreads, AT_BWDL_SMEM, stream>>>(tl, q);  // dQ
+    CLIPN_CHECK_CUDA(cudaGetLastError());
+    return CLIPN_OK;
+  }
   AttnBwdParams p;
   p.L = seq; p.B = batch; p.H = heads; p.D = heads * 64;
   p.G = seq <= 64 ? 2 : 1;
