@@ -149,7 +149,7 @@ def logits_gemm_roofline(sig_time, sig_count, peak_tflops):
             "avg_launch_ms": ms / n, "shape_mnk": [list(s[:3]) for s in lse_sigs]}
 
 
-def workload_config(model, batch, world, siglip=False, ckpt=False, optimizer="native"):
+def workload_config(model, batch, world, siglip=False, ckpt=False, optimizer="native", grad_sync="native"):
     """The `config` object of the native arm's JSON line."""
     if siglip:
         loss = "SigLipLoss, peer text/image blocks read in place (no neighbour exchange)"
@@ -157,7 +157,9 @@ def workload_config(model, batch, world, siglip=False, ckpt=False, optimizer="na
         loss = "ClipLoss local_loss" + (" + gather_with_grad, gather fused into the logits GEMM" if world > 1 else " only")
     return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, {loss}"
                         + (", grad-checkpointed blocks" if ckpt else ""),
-            "global_batch": world * batch, "parallelism": f"dp{world}",
+            "global_batch": world * batch,
+            "parallelism": f"dp{world}" + ("" if world == 1 else (" (per-block gradient all-reduce from the tower backward)"
+                                                                  if grad_sync == "native" else " (torch DDP)")),
             "optimizer": "AdamW multi-tensor, one launch (libclipn)" if optimizer == "native" else "AdamW fused (torch)",
             "cache": "inputs (>= 1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"}
 
@@ -237,6 +239,9 @@ def main():
                     help="BASELINE config 5: SigLipLoss, init_logit_scale=ln 10, init_logit_bias=-10 (main.py:259-261)")
     ap.add_argument("--optimizer", default="native", choices=["native", "torch"],
                     help="native: libclipn multi-tensor AdamW (one launch); torch: torch.optim.AdamW(fused=True)")
+    ap.add_argument("--grad-sync", default="native", choices=["native", "ddp"],
+                    help="N > 1: native = NativeCLIP.enable_grad_sync() (per-block all-reduce issued by the tower backward); "
+                         "ddp = torch DistributedDataParallel as the reference wraps it (base_task.py:227)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity block (outside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -306,7 +311,10 @@ def main():
         opt = torch.optim.AdamW(groups, lr=5e-4, betas=(0.9, 0.98), eps=1e-6, fused=True)
     module = model
     if world > 1:
-        module = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], bucket_cap_mb=200)
+        if args.grad_sync == "native":
+            model.enable_grad_sync()
+        else:
+            module = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], bucket_cap_mb=200)
 
     cfg = O.CONFIGS[args.model]
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
@@ -448,7 +456,8 @@ def main():
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": workload_config(args.model, B, world, args.siglip, args.grad_checkpointing, args.optimizer),
+            "config": workload_config(args.model, B, world, args.siglip, args.grad_checkpointing, args.optimizer,
+                                      args.grad_sync),
             "roofline": {"bound": "tensor", "kernel": top_name,
                          "share_of_step": (sig_time[top] / args.steps) / ms_step if top else None,
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",

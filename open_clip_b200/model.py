@@ -114,17 +114,49 @@ class _TowerFn(torch.autograd.Function):
         arena = model._grad_arena(which)
         arena["flat32"].zero_()
         G = arena["views32"]
+        # The fp32 arena is this node's ACCUMULATOR only; what autograd receives are views of two buffers owned by
+        # this call: one bf16 cast of the low-precision segment, one copy of the fp32 segment.  The arena can therefore
+        # be zeroed and refilled by the next backward of this tower — another micro-batch (`--accum-freq`,
+        # train.py:236-311), or a second use of the tower in the SAME graph (multi-view / multi-caption losses) whose
+        # first gradients still sit in the engine's input buffers.
+        n_lowp = arena["n_lowp"]
+        out16 = torch.empty_like(arena["flat16"]) if n_lowp else None
+        out32 = torch.empty_like(arena["flat32"][n_lowp:])
+        sync = model._grad_sync
+
+        def finalize(lo16, hi16, lo32, hi32):
+            """arena slices -> the per-call gradient buffers (+ asynchronous averaging all-reduce under grad sync)"""
+            if hi16 > lo16:
+                ops.cast_f32_to_bf16(arena["flat32"][lo16:hi16], out=out16[lo16:hi16])
+                if sync is not None:
+                    sync.reduce(out16[lo16:hi16])
+            if hi32 > lo32:
+                out32[lo32 - n_lowp:hi32 - n_lowp].copy_(arena["flat32"][lo32:hi32])
+                if sync is not None:
+                    sync.reduce(out32[lo32 - n_lowp:hi32 - n_lowp])
+
+        done16, done32 = [], []
+        if sync is not None:
+            spans = arena["block_spans"]
+
+            def on_block(pre):
+                lo16, hi16, lo32, hi32 = spans[pre]
+                finalize(lo16, hi16, lo32, hi32)
+                done16.append((lo16, hi16))
+                done32.append((lo32, hi32))
+            ctx.saved.extra["on_block_grads_ready"] = on_block
         bwd = tower.vision_backward if which == "visual" else tower.text_backward
         bwd(P, G, cfg, ctx.saved, dfeat, model._scratch[which])
         ctx.saved = None
-        # The fp32 arena is this node's ACCUMULATOR only; what autograd receives are views of two buffers owned by
-        # this call: one bf16 cast of the low-precision segment, one copy of the fp32 segment (2 launches, no
-        # per-parameter copies).  The arena can therefore be zeroed and refilled by the next backward of this tower —
-        # another micro-batch (`--accum-freq`, train.py:236-311), or a second use of the tower in the SAME graph
-        # (multi-view / multi-caption losses) whose first gradients still sit in the engine's input buffers.
-        n_lowp = arena["n_lowp"]
-        out16 = ops.cast_f32_to_bf16(arena["flat32"][:n_lowp], out=torch.empty_like(arena["flat16"])) if n_lowp else None
-        out32 = arena["flat32"][n_lowp:].clone()
+        # whatever the block callbacks did not cover (embeddings, head; everything without grad sync): the gaps
+        for (seg_lo, seg_hi, done, is16) in ((0, n_lowp, done16, True), (n_lowp, arena["flat32"].numel(), done32, False)):
+            cur = seg_lo
+            for lo, hi in sorted(done) + [(seg_hi, seg_hi)]:
+                if lo > cur:
+                    finalize(cur, lo, 0, 0) if is16 else finalize(0, 0, cur, lo)
+                cur = max(cur, hi)
+        if sync is not None:
+            sync.wait()
         grads = []
         for n, p in zip(names, ctx.P.values()):
             if not p.requires_grad:
@@ -134,6 +166,35 @@ class _TowerFn(torch.autograd.Function):
             src = out16[off:off + k] if p.dtype == BF16 else out32[off - n_lowp:off - n_lowp + k]
             grads.append(src.view(p.shape))
         return (None, None, None, None, None, *grads)
+
+
+class GradSync:
+    """Data-parallel gradient averaging driven by the towers' own backward (replaces DistributedDataParallel,
+    base_task.py:227, for NativeCLIP): every residual block's slice of the flat gradient buffers is all-reduced
+    (NCCL, asynchronously, on NCCL's stream) the moment that block's backward has finished, so the exchange overlaps the
+    remaining backward instead of starting when a whole tower's autograd node returns.  Scalars outside the towers
+    (logit_scale, logit_bias) are averaged by post-accumulate hooks.  Average = DDP's convention (sum / world)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.avg = dist.get_backend(self.group) == "nccl"  # gloo has no AVG: sum, then scale
+        self.pending = []
+
+    def reduce(self, t: torch.Tensor):
+        if self.world == 1:
+            return
+        op = self.dist.ReduceOp.AVG if self.avg else self.dist.ReduceOp.SUM
+        self.pending.append((self.dist.all_reduce(t, op=op, group=self.group, async_op=True), t))
+
+    def wait(self):
+        for work, t in self.pending:
+            work.wait()
+            if not self.avg:
+                t.div_(self.world)
+        self.pending.clear()
 
 
 class NativeCLIP(nn.Module):
@@ -245,6 +306,7 @@ class NativeCLIP(nn.Module):
         self._scratch = {"visual": tower.Scratch(), "text": tower.Scratch()}
         self._arenas: Dict[str, dict] = {}
         self.grad_checkpointing = False
+        self._grad_sync: Optional[GradSync] = None
 
     def _grad_arena(self, which: str) -> dict:
         """Flat fp32 gradient accumulators for one tower (low-precision params first)."""
@@ -266,10 +328,39 @@ class NativeCLIP(nn.Module):
                 v32[n] = flat32[off:off + k].view(params[n].shape)
                 offsets[n] = (off, k)
                 off += pad(k)
+            # per residual block: [lo, hi) of its parameters inside the bf16 segment and inside the fp32 segment
+            # (named_parameters() order keeps a block's tensors together in each segment)
+            spans = {}
+            for n in lowp + highp:
+                if ".resblocks." not in n:
+                    continue
+                pre = n[:n.index(".resblocks.") + len(".resblocks.")] + n.split(".resblocks.")[1].split(".")[0]
+                o, k = offsets[n]
+                sp = spans.setdefault(pre, [n_lowp, 0, total, n_lowp])
+                if n in lowp:
+                    sp[0], sp[1] = min(sp[0], o), max(sp[1], o + pad(k))
+                else:
+                    sp[2], sp[3] = min(sp[2], o), max(sp[3], o + pad(k))
+            for pre, sp in spans.items():
+                sp[1], sp[3] = min(sp[1], n_lowp), min(sp[3], total)
             # flat16 is only the shape/dtype template of the per-call bf16 gradient buffer (never written)
-            a = {"flat32": flat32, "flat16": flat16, "views32": v32, "offsets": offsets, "n_lowp": n_lowp}
+            a = {"flat32": flat32, "flat16": flat16, "views32": v32, "offsets": offsets, "n_lowp": n_lowp,
+                 "block_spans": {k: tuple(v) for k, v in spans.items()}}
             self._arenas[which] = a
         return a
+
+    def enable_grad_sync(self, group=None) -> "GradSync":
+        """Average gradients across the data-parallel group from inside the backward (per-block overlap) INSTEAD of
+        wrapping the module in DistributedDataParallel.  Parameters must already be identical on all ranks."""
+        self._grad_sync = GradSync(group)
+        sync = self._grad_sync
+        for p in (self.logit_scale, self.logit_bias):
+            if p is not None:
+                def hook(param, sync=sync):
+                    sync.reduce(param.grad)
+                    sync.wait()
+                p.register_post_accumulate_grad_hook(hook)
+        return sync
 
     # ------------------------------------------------------------------ reference API surface
     def set_grad_checkpointing(self, enable: bool = True, impl: str = "inline"):

@@ -105,6 +105,7 @@ def _run_blocks(P, cfg: TowerCfg, x: torch.Tensor, B: int, ws: Scratch, saved: O
 
 
 def _run_blocks_backward(P, G, cfg: TowerCfg, saved: TowerSaved, dx: torch.Tensor, B: int, ws: Scratch):
+    on_block = saved.extra.get("on_block_grads_ready")  # model.py: per-block gradient all-reduce (native grad sync)
     for i in reversed(range(cfg.layers)):
         pre = f"{cfg.prefix}.resblocks.{i}"
         s = saved.blocks[i]
@@ -113,6 +114,8 @@ def _run_blocks_backward(P, G, cfg: TowerCfg, saved: TowerSaved, dx: torch.Tenso
         dx = block_backward(P, G, pre, cfg, s, dx, B, ws)
         saved.blocks[i] = None  # free activations as we go
         del s
+        if on_block is not None:
+            on_block(pre)  # every gradient of this block is final: its all-reduce overlaps the next block's backward
     return dx
 
 

@@ -177,3 +177,56 @@ def test_all_gather_vectors_gloo_world2():
     expect = torch.tensor([[0, 1, 2, 100, 101, 102], [3, 4, 5, 103, 104, 105]], dtype=torch.float32).numpy()
     for r in range(2):
         assert (res[r] == expect).all()
+
+
+def _grad_sync_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from open_clip_b200 import ops, tower
+    from open_clip_b200.model import CONFIGS, NativeCLIP, _TowerFn
+    torch.manual_seed(0)
+    c = CONFIGS["tiny"]
+    m = NativeCLIP(c["embed_dim"], c["vision_cfg"], c["text_cfg"], device="cpu")
+    m.enable_grad_sync()
+    order = []
+
+    def fake_fwd(P, cfg, inp, normalize, ws, save, checkpoint=False):
+        return torch.zeros(inp.shape[0], cfg.embed_dim), (tower.TowerSaved(batch=inp.shape[0]) if save else None)
+
+    def fake_bwd(P, G, cfg, saved, dfeat, ws):
+        # the real schedule: head, blocks last -> first (callback after each), embeddings
+        for name, g in G.items():
+            g.fill_(float(rank + 1) * (1.0 + (hash(name) % 7)))
+        for i in reversed(range(cfg.layers)):
+            pre = f"{cfg.prefix}.resblocks.{i}"
+            order.append(pre)
+            saved.extra["on_block_grads_ready"](pre)
+
+    tower.vision_forward, tower.vision_backward = fake_fwd, fake_bwd
+    ops.cast_f32_to_bf16 = lambda x, out=None: out.copy_(x.to(torch.bfloat16))
+    params = dict(m.named_parameters())
+    names = m._tower_param_names["visual"]
+    plist = [params[n] for n in names]
+    _TowerFn.apply(m, "visual", True, True, torch.zeros(2, 3, 64, 64), *plist).sum().backward()
+    want = {n: (1 + 2) / 2.0 * (1.0 + (hash(n) % 7)) for n in names}   # mean over the two ranks
+    ok = all(abs(float(p.grad.float().mean()) - want[n]) < 2e-2 * want[n] and p.grad.dtype == p.dtype
+             for n, p in zip(names, plist))
+    q.put((rank, ok, order))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_native_grad_sync_averages_per_block_gloo_world2():
+    """NativeCLIP.enable_grad_sync(): the tower backward all-reduces each residual block's gradient slices as soon as
+    the block is done and whatever the callbacks did not cover at the end; result = mean over ranks, dtype preserved."""
+    os.environ["PYTHONHASHSEED"] = "0"
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_sync_worker, args=(r, 2, 29735, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=180) for _ in range(2)]
+    [p.join() for p in procs]
+    for rank, ok, order in res:
+        assert ok, rank
+        assert order == ["visual.transformer.resblocks.1", "visual.transformer.resblocks.0"]

@@ -19,6 +19,12 @@ for _ in range(3):
         ops.gemm(x, wpr, b_mn=True, epilogue=L.EPI_DGELU, aux=x4, out=o4, col_sum=cs)
     elif which == "gelu":
         ops.gemm(x, wfc, bias=b4, epilogue=L.EPI_BIAS_GELU, out=o4, out2=o4b)
+    elif which == "wgrad":     # split-K weight gradient (both operands MN-major, TMA reduce-add)
+        gw = torch.zeros(4 * d, d, device="cuda")
+        ops.gemm(x4, x, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=gw, splits=ops.wgrad_splits(4 * d, d, M))
+    elif which == "resid":     # out_proj / c_proj forward with the residual add
+        b1 = torch.zeros(d, device="cuda", dtype=bf)
+        ops.gemm(x4, wpr, bias=b1, aux=x, epilogue=L.EPI_BIAS_RESID, out=o1)
     elif which == "gelugrad":  # forward c_fc GEMM of the default (fast) activation mode: writes gelu'(h) and gelu(h)
         ops.gemm(x, wfc, bias=b4, epilogue=L.EPI_BIAS_GELU_GRAD, out=o4, out2=o4b)
     elif which == "mulaux":    # backward c_proj dgrad x saved gelu'(h) + fused c_fc bias gradient
