@@ -158,8 +158,9 @@ def workload_config(model, batch, world, siglip=False, ckpt=False, optimizer="na
     return {"workload": f"{model} bf16, local batch {batch}, {world}xB200, {loss}"
                         + (", grad-checkpointed blocks" if ckpt else ""),
             "global_batch": world * batch,
-            "parallelism": f"dp{world}" + ("" if world == 1 else (" (per-block gradient all-reduce from the tower backward)"
-                                                                  if grad_sync == "native" else " (torch DDP)")),
+            "parallelism": f"dp{world}",
+            "grad_sync": None if world == 1 else ("per-block NCCL all-reduce issued by the tower backward (libclipn arenas)"
+                                                  if grad_sync == "native" else "torch DistributedDataParallel"),
             "optimizer": "AdamW multi-tensor, one launch (libclipn)" if optimizer == "native" else "AdamW fused (torch)",
             "cache": "inputs (>= 1.2 GB/step) and activations exceed the 126 MB L2; no explicit flush"}
 
