@@ -315,23 +315,47 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
           for (int j = 0; j < nchunk; ++j) {
             float v[32];
             tmem_ld_32x32(t_row + cbase + j * 32, v);
+            if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {  // every key of the chunk visible to every row of the warp
+              float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, (j * 32 + i < kmax) ? v[i] * p.scale_log2 : -INFINITY);
+              for (int i = 4; i < 32; i += 4) {
+                m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+              }
+              m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2);  // scale > 0: max commutes with it
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) m = fmaxf(m, (j * 32 + i < kmax) ? v[i] * p.scale_log2 : -INFINITY);
+            }
           }
         }
         if (do_exp) {
           if (n_p > 0) mbar_wait(&pv_done[g], (n_p - 1) & 1);  // the previous PV has finished reading the P tile
+          const f32x2 sc2 = f2_splat(p.scale_log2), nm2 = f2_splat(-m);
           for (int j = 0; j < nchunk; ++j) {
             float v[32];
             tmem_ld_32x32(t_row + cbase + j * 32, v);
-            float s0 = 0.f, s1 = 0.f;
+            f32x2 acc2 = f2_splat(0.f);
+            if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              v[i] = (j * 32 + i < kmax) ? ex2_approx(fmaf(v[i], p.scale_log2, -m)) : 0.f;
-              v[i + 1] = (j * 32 + i + 1 < kmax) ? ex2_approx(fmaf(v[i + 1], p.scale_log2, -m)) : 0.f;
-              s0 += v[i];
-              s1 += v[i + 1];
+              for (int i = 0; i < 32; i += 2) {
+                float a0, a1;
+                f2_unpack(f2_fma(f2_pack(v[i], v[i + 1]), sc2, nm2), a0, a1);
+                v[i] = ex2_approx(a0);
+                v[i + 1] = ex2_approx(a1);
+                acc2 = f2_add(acc2, f2_pack(v[i], v[i + 1]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                float a0, a1;
+                f2_unpack(f2_fma(f2_pack(v[i], v[i + 1]), sc2, nm2), a0, a1);
+                v[i] = (j * 32 + i < kmax) ? ex2_approx(a0) : 0.f;
+                v[i + 1] = (j * 32 + i + 1 < kmax) ? ex2_approx(a1) : 0.f;
+                acc2 = f2_add(acc2, f2_pack(v[i], v[i + 1]));
+              }
             }
+            float s0, s1;
+            f2_unpack(acc2, s0, s1);
             l += s0 + s1;
             const int c0 = cbase + j * 32;  // first column of this chunk inside the P tile
             uint8_t* rowp = pbuf + (c0 >> 6) * 16384 + r * 128;
@@ -408,7 +432,7 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
 // dK over K, dV over V) by three TMA stores; the in_proj bias gradient (column sums of dqkv) is accumulated per head
 // in shared memory and flushed with one atomicAdd per column when the CTA's contiguous item range changes head.
 // ===================================================================================================
-constexpr int AT_BWD_SMEM = 2 * 4 * AT_TILE + 2 * AT_P + 192 * 4 + 256 + 1024;
+constexpr int AT_BWD_SMEM = 2 * 5 * AT_TILE + 2 * AT_P + 192 * 4 + 256 + 1024;
 static_assert(AT_BWD_SMEM <= 227 * 1024, "attention bwd smem budget");
 
 struct AttnBwdParams {
@@ -422,6 +446,7 @@ struct AttnBwdParams {
 struct alignas(64) AttnBwdMaps {
   CUtensorMap qkv;   // [B][L][3D] loads
   CUtensorMap dout;  // [B][L][D]  loads
+  CUtensorMap out;   // [B][L][D]  loads (forward output)
   CUtensorMap dqkv;  // [B][L][3D] stores
 };
 
@@ -445,8 +470,8 @@ __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* in_s = smem;                     // [2 stages][Q, K, V, dO]
-  uint8_t* p_s = in_s + 2 * 4 * AT_TILE;    // P tile
+  uint8_t* in_s = smem;                     // [2 stages][Q, K, V, dO, O]
+  uint8_t* p_s = in_s + 2 * 5 * AT_TILE;    // P tile
   uint8_t* ds_s = p_s + AT_P;               // dS tile
   float* bias_s = reinterpret_cast<float*>(ds_s + AT_P);  // [3][64] per-head bias-gradient accumulators
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 192);
@@ -506,12 +531,13 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         const int n = idx - i0, stage = n & 1;
         const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
         if (n >= 2) mbar_wait(&in_empty[stage], ((n >> 1) - 1) & 1);
-        uint8_t* st = in_s + stage * 4 * AT_TILE;
-        mbar_expect_tx(&in_full[stage], 4 * AT_TILE);
+        uint8_t* st = in_s + stage * 5 * AT_TILE;
+        mbar_expect_tx(&in_full[stage], 5 * AT_TILE);
         tma_load_3d(st, &tm.qkv, &in_full[stage], h * 64, 0, b0);
         tma_load_3d(st + AT_TILE, &tm.qkv, &in_full[stage], p.D + h * 64, 0, b0);
         tma_load_3d(st + 2 * AT_TILE, &tm.qkv, &in_full[stage], 2 * p.D + h * 64, 0, b0);
         tma_load_3d(st + 3 * AT_TILE, &tm.dout, &in_full[stage], h * 64, 0, b0);
+        tma_load_3d(st + 4 * AT_TILE, &tm.out, &in_full[stage], h * 64, 0, b0);  // O: D = rowsum(dO o O)
       }
     }
   } else if (warp == 1) {
@@ -521,11 +547,12 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       const uint32_t id_t = umma_idesc_bf16(128, 64, 1, 1);    // [keys x 64] = A^T (MN-major) x B (MN-major), K = queries
       const uint32_t id_q = umma_idesc_bf16(128, 64, 0, 1);    // [queries x 64] = A (K-major) x B (MN-major), K = keys
       const uint32_t sp = smem_u32(p_s), sds = smem_u32(ds_s);
-      for (int idx = i0; idx < i1; ++idx) {
-        const int n = idx - i0, stage = n & 1;
-        const uint32_t sq = smem_u32(in_s + stage * 4 * AT_TILE), sk = sq + AT_TILE, sv = sq + 2 * AT_TILE, sdo = sq + 3 * AT_TILE;
+      // S / dP of item n+1 are issued right behind the output MMAs of item n (their TMEM columns are free as soon as
+      // item n's P / dS are in shared memory), so the softmax-gradient warps find them ready after item n's epilogue
+      auto issue_sdp = [&](int n) {
+        const int stage = n & 1;
+        const uint32_t sq = smem_u32(in_s + stage * 5 * AT_TILE), sk = sq + AT_TILE, sv = sq + 2 * AT_TILE, sdo = sq + 3 * AT_TILE;
         mbar_wait(&in_full[stage], (n >> 1) & 1);
-        if (n > 0) mbar_wait(acc_free, (n - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -535,7 +562,13 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
           umma_bf16(tmem_base + 128, umma_smem_desc(sdo + k * 32, 16, 1024), umma_smem_desc(sv + k * 32, 16, 1024), id_s,
                     k > 0);
         umma_commit(sdp_full);
+      };
+      if (i0 < i1) issue_sdp(0);
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, stage = n & 1;
+        const uint32_t sq = smem_u32(in_s + stage * 5 * AT_TILE), sk = sq + AT_TILE, sdo = sq + 3 * AT_TILE;
         mbar_wait(pds_full, n & 1);
+        if (n > 0) mbar_wait(acc_free, (n - 1) & 1);  // the previous item's dV / dK / dQ have been read out of TMEM
         tc_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dV[key, d] = sum_q P[q, key] dO[q, d]
           umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, 16384, 1024), umma_smem_desc(sdo + kk * 2048, 8192, 1024),
@@ -547,6 +580,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
           umma_bf16(tmem_base + 384, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
                     umma_smem_desc(sk + kk * 2048, 8192, 1024), id_q, kk > 0);
         umma_commit(out_full);
+        if (idx + 1 < i1) issue_sdp(n + 1);
       }
     }
   } else if (warp >= 4) {
@@ -572,7 +606,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         if (cur_h >= 0) flush_bias();
         cur_h = h;
       }
-      uint8_t* st = in_s + stage * 4 * AT_TILE;
+      uint8_t* st = in_s + stage * 5 * AT_TILE;
       const int seq = p.G == 2 ? (r >> 6) : 0;
       const int qi = p.G == 2 ? (r & 63) : r;
       const int b = b0 + seq;
@@ -580,17 +614,17 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       const int cbase = seq * 64;
       int kmax = p.L;
       if (p.causal) kmax = qi + 1 < kmax ? qi + 1 : kmax;
-      // D = rowsum(dO o O): dO row from the staged tile, O row from global memory (128 contiguous bytes)
+      // D = rowsum(dO o O): both rows from the staged tiles
       mbar_wait(&in_full[stage], (n >> 1) & 1);
       float lse2 = 0.f, drow = 0.f;
       if (valid) {
         lse2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt;
-        const uint4* orow = reinterpret_cast<const uint4*>(p.out + (static_cast<int64_t>(b) * p.L + qi) * p.D + h * 64);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float a[8], d8[8];
-          unpack_bf16x8(__ldg(orow + c), a);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 3 * AT_TILE + r * 128 + ((c ^ (r & 7)) << 4)), d8);
+          const int sw = (c ^ (r & 7)) << 4;
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 4 * AT_TILE + r * 128 + sw), a);
+          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 3 * AT_TILE + r * 128 + sw), d8);
 #pragma unroll
           for (int i = 0; i < 8; ++i) drow = fmaf(a[i], d8[i], drow);
         }
@@ -1096,6 +1130,8 @@ int attention_tc_bwd(const void* qkv, const void* out, const void* dout, const f
   int rc = make_tmap_3d(&tm.qkv, qkv, 2, d3, seq, batch, d3 * 2, d3 * 2 * seq, 64, p.RB, p.G, 128);
   if (rc) return rc;
   rc = make_tmap_3d(&tm.dout, dout, 2, d1, seq, batch, d1 * 2, d1 * 2 * seq, 64, p.RB, p.G, 128);
+  if (rc) return rc;
+  rc = make_tmap_3d(&tm.out, out, 2, d1, seq, batch, d1 * 2, d1 * 2 * seq, 64, p.RB, p.G, 128);
   if (rc) return rc;
   rc = make_tmap_3d(&tm.dqkv, dqkv, 2, d3, seq, batch, d3 * 2, d3 * 2 * seq, 64, p.RB, p.G, 128);
   if (rc) return rc;

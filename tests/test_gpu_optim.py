@@ -1,4 +1,4 @@
-"""GPU parity: NativeAdamW (one multi-tensor launch) vs torch.optim.AdamW with the reference's groups and ViT defaults
+"""GPU parity: NativeAdamW (one multi-tensor launch) vs torch.optim.AdamW(fused=True) with the reference's groups and ViT defaults
 (open_clip_train/params.py:5-9: lr 5e-4, betas (0.9, 0.98), eps 1e-6, wd 0.2 / 0) over several steps, for bf16 and
 fp32 parameters of awkward sizes (vector tails, unaligned views).  Tolerance: fp32 parameters 1e-6 relative; bf16
 parameters may differ by one bf16 rounding of an fp32 update computed in a different association (<= 1 ulp)."""
@@ -27,7 +27,9 @@ def test_native_adamw_matches_torch_adamw():
     a, b = _params(0), _params(0)
     mk = lambda ps: [{"params": [p for p in ps if p.ndim < 2], "weight_decay": 0.0},
                      {"params": [p for p in ps if p.ndim >= 2], "weight_decay": 0.2}]
-    ref = torch.optim.AdamW(mk(a), lr=5e-4, betas=(0.9, 0.98), eps=1e-6)
+    # fused=True is the fp32-opmath implementation (one rounding per stored element); torch's default foreach path does
+    # the arithmetic of bf16 parameters in bf16, several roundings per step
+    ref = torch.optim.AdamW(mk(a), lr=5e-4, betas=(0.9, 0.98), eps=1e-6, fused=True)
     nat = NativeAdamW(mk(b), lr=5e-4, betas=(0.9, 0.98), eps=1e-6)
     g = torch.Generator().manual_seed(1)
     for step in range(6):
