@@ -481,7 +481,8 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   uint64_t* pds_full = bars + 5;  // P and dS in shared memory (8 warps)
   uint64_t* out_full = bars + 6;  // dV, dK, dQ in TMEM
   uint64_t* acc_free = bars + 7;  // TMEM read by the epilogue (8 warps)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> store warp
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -503,6 +504,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     mbar_init(pds_full, 8);
     mbar_init(out_full, 1);
     mbar_init(acc_free, 8);
+    mbar_init(staged, 8);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -583,11 +585,27 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         if (idx + 1 < i1) issue_sdp(n + 1);
       }
     }
+  } else if (warp == 3) {
+    if (elect_one()) {
+      // ===================== store warp: three TMA stores per item; its read-wait stalls nobody else =====================
+      for (int idx = i0; idx < i1; ++idx) {
+        const int n = idx - i0, stage = n & 1;
+        const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
+        uint8_t* st = in_s + stage * 5 * AT_TILE;
+        mbar_wait(staged, n & 1);
+        tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
+        tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
+        tma_store_3d(&tm.dqkv, st + 2 * AT_TILE, 2 * p.D + h * 64, 0, b0);
+        tma_store_commit();
+        tma_store_wait_read<0>();       // the stage's tiles have been read: the producer may refill them
+        mbar_arrive(&in_empty[stage]);
+      }
+      tma_store_wait_all<0>();
+    }
   } else if (warp >= 4) {
     // ===================== softmax-gradient + epilogue warps: (TMEM lane quarter, column half) =====================
     const int quarter = (warp - 4) & 3, half = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;
-    const bool leader = warp == 4 && lane == 0;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     int cur_h = -1;
     auto flush_bias = [&]() {  // all 256 threads
@@ -692,19 +710,12 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_free);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (leader) {
-        tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
-        tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
-        tma_store_3d(&tm.dqkv, st + 2 * AT_TILE, 2 * p.D + h * 64, 0, b0);
-        tma_store_commit();
-        tma_store_wait_read<0>();       // the stage's tiles have been read: the producer may refill them
-        mbar_arrive(&in_empty[stage]);
+      if (lane == 0) {
+        mbar_arrive(acc_free);
+        mbar_arrive(staged);
       }
     }
     if (cur_h >= 0) flush_bias();
-    if (leader) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

@@ -285,11 +285,16 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
     float cl2[32];
     if (p.col_w != 0.f) {
       // column LSE vector: 32 consecutive floats, the same for every lane (broadcast loads through L1)
-      const float4* src = reinterpret_cast<const float4*>(p.col_lse + col);
+      if (nvalid == 32 && (reinterpret_cast<uintptr_t>(p.col_lse + col) & 15) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(p.col_lse + col);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 t = (i * 4 < nvalid) ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        cl2[4 * i] = t.x * kLog2e; cl2[4 * i + 1] = t.y * kLog2e; cl2[4 * i + 2] = t.z * kLog2e; cl2[4 * i + 3] = t.w * kLog2e;
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(src + i);
+          cl2[4 * i] = t.x * kLog2e; cl2[4 * i + 1] = t.y * kLog2e; cl2[4 * i + 2] = t.z * kLog2e; cl2[4 * i + 3] = t.w * kLog2e;
+        }
+      } else {  // ragged tail / a vector that is not 16-byte aligned (batch not a multiple of 4)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cl2[i] = (i < nvalid) ? __ldg(p.col_lse + col + i) * kLog2e : 0.f;
       }
     }
     const float shift = (1.f + p.col_w) / static_cast<float>(p.n);
@@ -861,9 +866,12 @@ int peer_gemm_launch(const PeerGemmDesc& d, cudaStream_t stream) {
 int gemm_launch(const clipn_gemm_desc& d, const void* const* b_ptrs, int b_maps, int64_t b_rows_per_map, bool use_ref,
                 cudaStream_t stream) {
   CLIPN_REQUIRE(d.m > 0 && d.n > 0 && d.k > 0, "gemm: empty problem");
-  CLIPN_REQUIRE(d.n % 8 == 0, "gemm: N must be a multiple of 8");
+  // the loss epilogues handle any N (per-element masks, TMA-clipped stores): a contrastive batch need not be a
+  // multiple of 8 (reference ClipLoss / SigLipLoss take any batch); the others read bias / aux vectors 8 at a time
+  const bool any_n = d.epilogue == CLIPN_EPI_LSE || d.epilogue == CLIPN_EPI_CLIP_DLOGITS || d.epilogue == CLIPN_EPI_SIGLIP;
+  CLIPN_REQUIRE(any_n || d.n % 8 == 0, "gemm: N must be a multiple of 8");
+  // row pitches must be 16-byte multiples for the TMA maps; the contraction length itself is free (TMA zero-fills)
   CLIPN_REQUIRE(d.lda % 8 == 0 && d.ldb % 8 == 0, "gemm: leading dims must be multiples of 8");
-  CLIPN_REQUIRE(d.k % 8 == 0 || (d.a_mn_major && d.b_mn_major), "gemm: K must be a multiple of 8 for K-major operands");
   CLIPN_REQUIRE(b_maps >= 1 && b_maps <= kMaxBMaps, "gemm: 1..8 B maps");
   const int ep = d.epilogue;
   const bool needs_c = !(ep == CLIPN_EPI_LSE || (ep == CLIPN_EPI_SIGLIP && d.c == nullptr));

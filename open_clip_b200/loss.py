@@ -13,8 +13,8 @@ sum over ALL ranks' losses) without moving any [N,E] gradient across NVLink.
 
 Supported envelope: any world size / batch; shapes or transports the fused kernel does not take (world > 8, several
 nodes, per-rank batch not a multiple of 128, embed dim not a multiple of 64) run the same math after an NCCL
-all-gather (comm.FeatureGather, mode "nccl").  Hard limits, raised as ClipnError: CUDA tensors only, W*B % 8 == 0,
-embed dim % 8 == 0.
+all-gather (comm.FeatureGather, mode "nccl").  Hard limits, raised as ClipnError: CUDA tensors only, embed dim % 8 == 0
+(any batch size: ragged d(logits) rows are padded to a 16-byte pitch internally).
 """
 from __future__ import annotations
 
@@ -37,9 +37,8 @@ def _check_inputs(name: str, image_features, text_features, world: int):
         raise ClipnError(f"{name}: image/text features must both be [B, E], got {tuple(image_features.shape)} and "
                          f"{tuple(text_features.shape)}")
     b, e = image_features.shape
-    if (b * world) % 8 != 0 or e % 8 != 0:
-        raise ClipnError(f"{name}: world*batch ({world}*{b}) and the embed dim ({e}) must be multiples of 8 "
-                         "(16-byte rows for the TMA tensor maps)")
+    if e % 8 != 0:
+        raise ClipnError(f"{name}: the embed dim ({e}) must be a multiple of 8 (16-byte rows for the TMA tensor maps)")
 
 
 def _gathered(module, img, txt, B, E, W):
@@ -119,10 +118,10 @@ class _ClipLossFn(torch.autograd.Function):
         mean_t = ops.colsum(all_txt, torch.zeros(E, dtype=F32, device=img.device)) / N
         mean_i = ops.colsum(all_img, torch.zeros(E, dtype=F32, device=img.device)) / N
         dl_i = ops.clip_dlogits(img, all_txt, scale, off, lse_i, all_lse_t if col_w else None, col_w, gscale, acc[0:2])
-        d_img = ops.clip_dfeat(dl_i, all_txt, scale, init=(mean_t - txt.float()) * coef)
+        d_img = ops.clip_dfeat(dl_i, all_txt, scale, n=N, init=(mean_t - txt.float()) * coef)
         del dl_i
         dl_t = ops.clip_dlogits(txt, all_img, scale, off, lse_t, all_lse_i if col_w else None, col_w, gscale, acc[2:4])
-        d_txt = ops.clip_dfeat(dl_t, all_img, scale, init=(mean_i - img.float()) * coef)
+        d_txt = ops.clip_dfeat(dl_t, all_img, scale, n=N, init=(mean_i - img.float()) * coef)
         del dl_t
         # d loss / d logit_scale = sum_{dir} sum (P_row - onehot) * <row, col> / (2B)   (own loss only)
         d_scale = (acc[0] + acc[2]) * ((1.0 / (2 * B)) / gscale)

@@ -365,10 +365,11 @@ def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscal
     _chk(rows, BF16, "dlogits.rows"); _chk(cols, BF16, "dlogits.cols")
     m, e = rows.shape
     n = cols.shape[0]
-    out = torch.empty((m, n), dtype=BF16, device=rows.device)
+    ld = (n + 7) // 8 * 8  # 16-byte row pitch for any batch size; columns [n, ld) are never written nor read
+    out = torch.empty((m, ld), dtype=BF16, device=rows.device)
     with _profiled((m, n, e, L.EPI_CLIP_DLOGITS, False, False)):
         _call(L.lib().clipn_clip_dlogits(rows.data_ptr(), cols.data_ptr(), m, n, e, 1.0, scale.data_ptr(), label_offset,
-                                           row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(), n,
+                                           row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(), ld,
                                            _ptr(scalar_acc), _stream()))
     return out
 
@@ -395,12 +396,13 @@ def siglip_dir(rows, cols, scale, bias, label_offset, gscale, loss_acc, scalar_a
     loss_acc / scalar_acc (optional) accumulate the value and d scale, d bias; returns d(logits) bf16 [m, n] or None."""
     m, e = rows.shape
     n = cols.shape[0]
-    dl = torch.empty((m, n), dtype=BF16, device=rows.device) if want_grad else None
+    ld = (n + 7) // 8 * 8
+    dl = torch.empty((m, ld), dtype=BF16, device=rows.device) if want_grad else None
     d = L.GemmDesc()
     d.a, d.lda, d.a_mn_major = rows.data_ptr(), e, 0
     d.b, d.ldb, d.b_mn_major = cols.data_ptr(), e, 0
     if dl is not None:
-        d.c, d.ldc = dl.data_ptr(), n
+        d.c, d.ldc = dl.data_ptr(), ld
     d.m, d.n, d.k = m, n, e
     d.epilogue, d.alpha, d.splits = L.EPI_SIGLIP, 1.0, 1
     d.alpha_dev, d.logit_bias_dev = scale.data_ptr(), bias.data_ptr()

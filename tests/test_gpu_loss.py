@@ -29,7 +29,7 @@ def path(request, monkeypatch):
 
 
 @pytest.mark.parametrize("b,e", [(8, 64), (32, 64), (128, 128), (200, 512), (1000, 512), (4096, 512), (520, 768),
-                                 (256, 1024), (64, 32)])
+                                 (256, 1024), (64, 32), (2, 768), (6, 64), (50, 512), (131, 64)])  # any batch size
 @pytest.mark.parametrize("feat_dtype", [BF16, F32])
 def test_clip_loss_value_and_grads(b, e, feat_dtype, path):
     i, t = _feats(b, e, 3)
@@ -102,7 +102,7 @@ def test_siglip_no_grad_forward_skips_the_gradient_gemms():
     assert abs(float(l0) - float(l1)) < 1e-3 * abs(float(l1)) + 1e-4
 
 
-@pytest.mark.parametrize("b,e", [(64, 32), (256, 512), (200, 128), (1000, 512)])
+@pytest.mark.parametrize("b,e", [(64, 32), (256, 512), (200, 128), (1000, 512), (6, 64), (131, 128)])
 def test_siglip_loss_value_and_grads(b, e, path):
     i, t = _feats(b, e, 5)
     scale, bias = torch.tensor(10.0, device="cuda"), torch.tensor(-10.0, device="cuda")
