@@ -586,57 +586,85 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       }
     }
   } else if (warp == 3) {
-    if (elect_one()) {
-      // ===================== store warp: three TMA stores per item; its read-wait stalls nobody else =====================
-      for (int idx = i0; idx < i1; ++idx) {
-        const int n = idx - i0, stage = n & 1;
-        const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
-        uint8_t* st = in_s + stage * 5 * AT_TILE;
-        mbar_wait(staged, n & 1);
+    // ===================== store warp: TMA stores + the in_proj bias gradient, off the compute warps' critical path ====
+    // Column sums of the STAGED (bf16-rounded) dQ and dV tiles: lane c owns columns 2c, 2c+1 and walks the 128 rows —
+    // a row's 32 lanes read its 128 bytes exactly once (conflict-free in the SW128 layout).  The K third is not summed:
+    // sum_key dS[q, key] = scale * (sum_key P dP - D sum_key P) = 0, a key bias has no gradient (softmax is invariant to
+    // a common shift of the keys).
+    float aq0 = 0.f, aq1 = 0.f, av0 = 0.f, av1 = 0.f;
+    int cur_h = -1;
+    auto flush = [&]() {
+      if (p.dbias != nullptr && cur_h >= 0) {
+        float* dq = p.dbias + cur_h * 64 + 2 * lane;
+        atomicAdd(dq, aq0);
+        atomicAdd(dq + 1, aq1);
+        atomicAdd(dq + 2 * p.D, av0);
+        atomicAdd(dq + 2 * p.D + 1, av1);
+      }
+      aq0 = aq1 = av0 = av1 = 0.f;
+    };
+    for (int idx = i0; idx < i1; ++idx) {
+      const int n = idx - i0, stage = n & 1;
+      const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
+      uint8_t* st = in_s + stage * 5 * AT_TILE;
+      if (h != cur_h) {
+        flush();
+        cur_h = h;
+      }
+      mbar_wait(staged, n & 1);
+      if (lane == 0) {
         tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
         tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
         tma_store_3d(&tm.dqkv, st + 2 * AT_TILE, 2 * p.D + h * 64, 0, b0);
         tma_store_commit();
+      }
+      if (p.dbias != nullptr) {
+        const int cw = (lane & 3) * 4;
+#pragma unroll 8
+        for (int r = 0; r < 128; ++r) {
+          const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + cw;
+          const uint32_t wq = *reinterpret_cast<const uint32_t*>(st + off);
+          const uint32_t wv = *reinterpret_cast<const uint32_t*>(st + 2 * AT_TILE + off);
+          aq0 += __uint_as_float(wq << 16);
+          aq1 += __uint_as_float(wq & 0xffff0000u);
+          av0 += __uint_as_float(wv << 16);
+          av1 += __uint_as_float(wv & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
         tma_store_wait_read<0>();       // the stage's tiles have been read: the producer may refill them
         mbar_arrive(&in_empty[stage]);
       }
-      tma_store_wait_all<0>();
+      __syncwarp();
     }
+    flush();
+    if (lane == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ===================== softmax-gradient + epilogue warps: (TMEM lane quarter, column half) =====================
     const int quarter = (warp - 4) & 3, half = (warp - 4) >> 2;
     const int r = quarter * 32 + lane;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    int cur_h = -1;
-    auto flush_bias = [&]() {  // all 256 threads
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int t = threadIdx.x - 128;
-      if (t < 192 && p.dbias != nullptr && cur_h >= 0) {
-        atomicAdd(p.dbias + (t >> 6) * p.D + cur_h * 64 + (t & 63), bias_s[t]);
-        bias_s[t] = 0.f;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    };
-    for (int idx = i0; idx < i1; ++idx) {
+    const int seq = p.G == 2 ? (r >> 6) : 0;
+    const int qi = p.G == 2 ? (r & 63) : r;
+    const int cbase = seq * 64;
+    int kmax = p.L;
+    if (p.causal) kmax = qi + 1 < kmax ? qi + 1 : kmax;
+    const int nchunk = p.G == 2 ? 2 : (p.L + 31) >> 5;   // 32-column chunks holding keys of this row's block
+    const int per = p.G == 2 ? 1 : 2;                    // chunks per column half
+    // per-item row constants (log-sum-exp, D = rowsum(dO o O)); computed one item AHEAD, in the window where the
+    // warps would otherwise only wait for the output MMAs
+    auto row_consts = [&](int idx, bool& valid, float& lse2, float& drow) {
       const int n = idx - i0, stage = n & 1;
-      const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
-      if (h != cur_h) {
-        if (cur_h >= 0) flush_bias();
-        cur_h = h;
-      }
-      uint8_t* st = in_s + stage * 5 * AT_TILE;
-      const int seq = p.G == 2 ? (r >> 6) : 0;
-      const int qi = p.G == 2 ? (r & 63) : r;
-      const int b = b0 + seq;
-      const bool valid = qi < p.L && b < p.B;
-      const int cbase = seq * 64;
-      int kmax = p.L;
-      if (p.causal) kmax = qi + 1 < kmax ? qi + 1 : kmax;
-      // D = rowsum(dO o O): both rows from the staged tiles
+      const int h = idx / p.nb, b = (idx % p.nb) * p.G + seq;
+      const uint8_t* st = in_s + stage * 5 * AT_TILE;
+      valid = qi < p.L && b < p.B;
+      lse2 = 0.f;
+      drow = 0.f;
+      float lse_v = 0.f;
+      if (valid) lse_v = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi);
       mbar_wait(&in_full[stage], (n >> 1) & 1);
-      float lse2 = 0.f, drow = 0.f;
       if (valid) {
-        lse2 = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float a[8], d8[8];
@@ -646,11 +674,17 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) drow = fmaf(a[i], d8[i], drow);
         }
+        lse2 = lse_v * kLog2eAt;
       }
+    };
+    bool valid = false, nvalid_row = false;
+    float lse2 = 0.f, drow = 0.f, nlse2 = 0.f, ndrow = 0.f;
+    if (i0 < i1) row_consts(i0, valid, lse2, drow);
+    for (int idx = i0; idx < i1; ++idx) {
+      const int n = idx - i0, stage = n & 1;
+      uint8_t* st = in_s + stage * 5 * AT_TILE;
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
-      const int nchunk = p.G == 2 ? 2 : (p.L + 31) >> 5;   // 32-column chunks holding keys of this row's block
-      const int per = p.G == 2 ? 1 : 2;                    // chunks per column half
       for (int jj = 0; jj < per; ++jj) {
         const int j = half * per + jj;
         if (j >= nchunk) break;
@@ -683,7 +717,8 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // ---- epilogue: dV | dK | dQ columns [half*32, half*32+32) of row r -> bf16 -> the stage's V | K | Q tile
+      if (idx + 1 < i1) row_consts(idx + 1, nvalid_row, nlse2, ndrow);  // overlaps the dV / dK / dQ MMAs
+      // ---- epilogue: dQ | dK | dV columns [half*32, half*32+32) of row r -> bf16 -> the stage's Q | K | V tile
       mbar_wait(out_full, n & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -696,15 +731,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
           float t8[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) t8[i] = v[q4 * 8 + i];
-          const uint4 pk = pack_bf16x8(t8);
-          *reinterpret_cast<uint4*>(dst + (((half * 4 + q4) ^ (r & 7)) << 4)) = pk;
-          unpack_bf16x8(pk, t8);  // the bias gradient sums the ROUNDED values (== column sums of the stored dqkv)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[q4 * 8 + i] = t8[i];
-        }
-        if (p.dbias != nullptr) {
-          const float cs = warp_transpose_sum(v);
-          atomicAdd(bias_s + part * 64 + half * 32 + lane, cs);
+          *reinterpret_cast<uint4*>(dst + (((half * 4 + q4) ^ (r & 7)) << 4)) = pack_bf16x8(t8);
         }
       }
       tc_fence_before();
@@ -714,8 +741,10 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         mbar_arrive(acc_free);
         mbar_arrive(staged);
       }
+      valid = nvalid_row;
+      lse2 = nlse2;
+      drow = ndrow;
     }
-    if (cur_h >= 0) flush_bias();
   }
 
   tc_fence_before();

@@ -214,9 +214,9 @@ def main():
         torch.save(model_goldens(open_clip, "ViT-L-14-336-d2", batch=8, seed=11),
                    os.path.join(gold_dir, "vitl14_336_d2_model.pt"))
     if "vitl14_full" in only:
-        # BASELINE config 4 at its real depth (24 + 12 blocks), batch 2: minutes of reference autograd on the CPU
+        # BASELINE config 4 at its real depth (24 + 12 blocks), batch 8: ~15 min of reference autograd on 8 CPU cores
         print("model goldens: ViT-L-14-336, full depth")
-        torch.save(model_goldens(open_clip, "ViT-L-14-336", batch=2, seed=13),
+        torch.save(model_goldens(open_clip, "ViT-L-14-336", batch=8, seed=13),
                    os.path.join(gold_dir, "vitl14_336_full_model.pt"))
     if "vitb16_siglip" in only:
         print("model goldens: ViT-B-16 + SigLipLoss")
