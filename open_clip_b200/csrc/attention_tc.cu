@@ -311,35 +311,54 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
         const int nchunk = (kv_valid + 31) >> 5;  // warp-uniform
         mbar_wait(&s_full[g], n_s & 1);
         tc_fence_after();
+        // TMEM reads are software-pipelined: chunk j+1 is requested before the math of chunk j (two register sets,
+        // the loop is written two chunks at a time so that the sets are never selected dynamically)
+        uint32_t ra[32], rb[32];
+        auto pipelined = [&](auto&& process) {
+          tmem_ld_32x32_issue(t_row + cbase, ra);
+          tmem_ld_wait(ra);
+          for (int j = 0; j < nchunk; j += 2) {
+            if (j + 1 < nchunk) tmem_ld_32x32_issue(t_row + cbase + (j + 1) * 32, rb);
+            process(ra, j);
+            if (j + 1 < nchunk) {
+              tmem_ld_wait(rb);
+              if (j + 2 < nchunk) tmem_ld_32x32_issue(t_row + cbase + (j + 2) * 32, ra);
+              process(rb, j + 1);
+              if (j + 2 < nchunk) tmem_ld_wait(ra);
+            }
+          }
+        };
         if (do_max) {
-          for (int j = 0; j < nchunk; ++j) {
-            float v[32];
-            tmem_ld_32x32(t_row + cbase + j * 32, v);
+          pipelined([&](uint32_t (&cur)[32], int j) {
             if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {  // every key of the chunk visible to every row of the warp
-              float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+              float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]), m2 = __uint_as_float(cur[2]),
+                    m3 = __uint_as_float(cur[3]);
 #pragma unroll
               for (int i = 4; i < 32; i += 4) {
-                m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+                m0 = fmaxf(m0, __uint_as_float(cur[i]));
+                m1 = fmaxf(m1, __uint_as_float(cur[i + 1]));
+                m2 = fmaxf(m2, __uint_as_float(cur[i + 2]));
+                m3 = fmaxf(m3, __uint_as_float(cur[i + 3]));
               }
               m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * p.scale_log2);  // scale > 0: max commutes with it
             } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) m = fmaxf(m, (j * 32 + i < kmax) ? v[i] * p.scale_log2 : -INFINITY);
+              for (int i = 0; i < 32; ++i)
+                m = fmaxf(m, (j * 32 + i < kmax) ? __uint_as_float(cur[i]) * p.scale_log2 : -INFINITY);
             }
-          }
+          });
         }
         if (do_exp) {
           if (n_p > 0) mbar_wait(&pv_done[g], (n_p - 1) & 1);  // the previous PV has finished reading the P tile
           const f32x2 sc2 = f2_splat(p.scale_log2), nm2 = f2_splat(-m);
-          for (int j = 0; j < nchunk; ++j) {
+          pipelined([&](uint32_t (&cur)[32], int j) {
             float v[32];
-            tmem_ld_32x32(t_row + cbase + j * 32, v);
             f32x2 acc2 = f2_splat(0.f);
             if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
                 float a0, a1;
-                f2_unpack(f2_fma(f2_pack(v[i], v[i + 1]), sc2, nm2), a0, a1);
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, nm2), a0, a1);
                 v[i] = ex2_approx(a0);
                 v[i + 1] = ex2_approx(a1);
                 acc2 = f2_add(acc2, f2_pack(v[i], v[i + 1]));
@@ -348,7 +367,7 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
                 float a0, a1;
-                f2_unpack(f2_fma(f2_pack(v[i], v[i + 1]), sc2, nm2), a0, a1);
+                f2_unpack(f2_fma(f2_pack(__uint_as_float(cur[i]), __uint_as_float(cur[i + 1])), sc2, nm2), a0, a1);
                 v[i] = (j * 32 + i < kmax) ? ex2_approx(a0) : 0.f;
                 v[i + 1] = (j * 32 + i + 1 < kmax) ? ex2_approx(a1) : 0.f;
                 acc2 = f2_add(acc2, f2_pack(v[i], v[i + 1]));
@@ -367,7 +386,7 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
               const int ch = ((c0 & 63) >> 3) + q4;
               *reinterpret_cast<uint4*>(rowp + ((ch ^ (r & 7)) << 4)) = pack_bf16x8(t8);
             }
-          }
+          });
           fence_proxy_async_smem();
         }
         tc_fence_before();
@@ -481,8 +500,9 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   uint64_t* pds_full = bars + 5;  // P and dS in shared memory (8 warps)
   uint64_t* out_full = bars + 6;  // dV, dK, dQ in TMEM
   uint64_t* acc_free = bars + 7;  // TMEM read by the epilogue (8 warps)
-  uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> store warp
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> warps 2 and 3
+  uint64_t* sums_done = bars + 9; // warp 2 -> warp 3
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -505,6 +525,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     mbar_init(out_full, 1);
     mbar_init(acc_free, 8);
     mbar_init(staged, 8);
+    mbar_init(sums_done, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -585,23 +606,22 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         if (idx + 1 < i1) issue_sdp(n + 1);
       }
     }
-  } else if (warp == 3) {
-    // ===================== store warp: TMA stores + the in_proj bias gradient, off the compute warps' critical path ====
-    // Column sums of the STAGED (bf16-rounded) dQ and dV tiles: lane c owns columns 2c, 2c+1 and walks the 128 rows —
-    // a row's 32 lanes read its 128 bytes exactly once (conflict-free in the SW128 layout).  The K third is not summed:
-    // sum_key dS[q, key] = scale * (sum_key P dP - D sum_key P) = 0, a key bias has no gradient (softmax is invariant to
-    // a common shift of the keys).
-    float aq0 = 0.f, aq1 = 0.f, av0 = 0.f, av1 = 0.f;
+  } else if (warp == 2 || warp == 3) {
+    // ===================== warps 2 / 3: TMA stores + the in_proj bias gradient, off the compute warps' critical path ====
+    // Column sums of the STAGED (bf16-rounded) tiles — warp 2: dQ, warp 3: dV (+ the three TMA stores).  Lane c owns
+    // columns 2c, 2c+1 and walks the 128 rows: a row's 32 lanes read its 128 bytes exactly once (conflict-free in the
+    // SW128 layout).  The K third is not summed: sum_key dS[q, key] = scale * (sum_key P dP - D sum_key P) = 0 — a key
+    // bias has no gradient (softmax is invariant to a common shift of the keys).
+    const int tile = warp == 2 ? 0 : 2;  // Q slot holds dQ, V slot holds dV
+    float a0 = 0.f, a1 = 0.f;
     int cur_h = -1;
     auto flush = [&]() {
       if (p.dbias != nullptr && cur_h >= 0) {
-        float* dq = p.dbias + cur_h * 64 + 2 * lane;
-        atomicAdd(dq, aq0);
-        atomicAdd(dq + 1, aq1);
-        atomicAdd(dq + 2 * p.D, av0);
-        atomicAdd(dq + 2 * p.D + 1, av1);
+        float* d = p.dbias + tile * p.D + cur_h * 64 + 2 * lane;
+        atomicAdd(d, a0);
+        atomicAdd(d + 1, a1);
       }
-      aq0 = aq1 = av0 = av1 = 0.f;
+      a0 = a1 = 0.f;
     };
     for (int idx = i0; idx < i1; ++idx) {
       const int n = idx - i0, stage = n & 1;
@@ -612,34 +632,39 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         cur_h = h;
       }
       mbar_wait(staged, n & 1);
-      if (lane == 0) {
+      if (warp == 3 && lane == 0) {
         tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
         tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
         tma_store_3d(&tm.dqkv, st + 2 * AT_TILE, 2 * p.D + h * 64, 0, b0);
         tma_store_commit();
       }
       if (p.dbias != nullptr) {
-        const int cw = (lane & 3) * 4;
+        const uint8_t* base = st + tile * AT_TILE + (lane & 3) * 4;
+        float b0s = 0.f, b1s = 0.f, c0s = 0.f, c1s = 0.f;  // four independent chains
 #pragma unroll 8
-        for (int r = 0; r < 128; ++r) {
-          const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + cw;
-          const uint32_t wq = *reinterpret_cast<const uint32_t*>(st + off);
-          const uint32_t wv = *reinterpret_cast<const uint32_t*>(st + 2 * AT_TILE + off);
-          aq0 += __uint_as_float(wq << 16);
-          aq1 += __uint_as_float(wq & 0xffff0000u);
-          av0 += __uint_as_float(wv << 16);
-          av1 += __uint_as_float(wv & 0xffff0000u);
+        for (int r = 0; r < 128; r += 2) {
+          const uint32_t w0 = *reinterpret_cast<const uint32_t*>(base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+          const uint32_t w1 = *reinterpret_cast<const uint32_t*>(base + (r + 1) * 128 + (((lane >> 2) ^ ((r + 1) & 7)) << 4));
+          b0s += __uint_as_float(w0 << 16);
+          b1s += __uint_as_float(w0 & 0xffff0000u);
+          c0s += __uint_as_float(w1 << 16);
+          c1s += __uint_as_float(w1 & 0xffff0000u);
         }
+        a0 += b0s + c0s;
+        a1 += b1s + c1s;
       }
       __syncwarp();
-      if (lane == 0) {
-        tma_store_wait_read<0>();       // the stage's tiles have been read: the producer may refill them
+      if (warp == 2) {
+        if (lane == 0) mbar_arrive(sums_done);  // the dQ tile has been summed
+      } else if (lane == 0) {
+        tma_store_wait_read<0>();       // the stage's tiles have been read by the stores ...
+        mbar_wait(sums_done, n & 1);    // ... and by warp 2: the producer may refill them
         mbar_arrive(&in_empty[stage]);
       }
       __syncwarp();
     }
     flush();
-    if (lane == 0) tma_store_wait_all<0>();
+    if (warp == 3 && lane == 0) tma_store_wait_all<0>();
   } else if (warp >= 4) {
     // ===================== softmax-gradient + epilogue warps: (TMEM lane quarter, column half) =====================
     const int quarter = (warp - 4) & 3, half = (warp - 4) >> 2;

@@ -218,7 +218,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
         __syncwarp();
         if (lane == 0) {
           if (rank == 0) mbar_arrive(&tmem_empty[acc]);
-          else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+          else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // publishes no memory: no MEMBAR
         }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -299,7 +299,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapSet tm, const GemmParams p_in) {
       __syncwarp();
       if (lane == 0) {
         if (rank == 0) mbar_arrive(&tmem_empty[acc]);
-        else mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+        else mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty[acc]), 0));  // publishes no memory: no MEMBAR
       }
       // LSE partial slabs are indexed by 128-column halves of the N tile, exactly like the single-CTA kernel
       epi_finish<EPI>(p, row, tn * 2 + h, st);
