@@ -22,6 +22,10 @@
 
 #include "common.cuh"
 
+#ifndef AT_PIPELINED_LD
+#define AT_PIPELINED_LD 0
+#endif
+
 namespace clipn {
 
 constexpr int kAtThreads = 384;
@@ -72,7 +76,7 @@ struct AtStream {
   int t;             // next step whose QK^T is to be issued
   bool active;       // a QK^T remains for the current item
   bool pv_pending;   // the PV of the last issued step is still to be issued
-  int pv_kt;
+  int pv_kt, pv_h, pv_b0;  // key tile / head / first sequence of the step that owes it
   bool pv_first, pv_last;
 };
 __device__ __forceinline__ void at_stream_init(AtStream& s, const AttnFwdParams& p, int g) {
@@ -82,24 +86,23 @@ __device__ __forceinline__ void at_stream_init(AtStream& s, const AttnFwdParams&
   s.t = 0;
   if (s.active) s.it = at_decode(p, s.idx);
 }
-// after the QK^T of step t has been issued
-__device__ __forceinline__ void at_stream_after_s(AtStream& s) {
+// after the QK^T of step t has been issued: records the PV this step owes (if any) and moves on — to the next step, or to
+// the group's next item when this was the item's last QK^T (the owed PV is issued later from the recorded copy)
+__device__ __forceinline__ void at_stream_after_s(AtStream& s, const AttnFwdParams& p) {
   int kt;
   bool do_max, do_exp;
   at_step(s.it, s.t, kt, do_max, do_exp);
   const bool last = s.t == s.it.T - 1;
+  s.pv_pending = do_exp;
   if (do_exp) {
-    s.pv_pending = true;
     s.pv_kt = kt;
+    s.pv_h = s.it.h;
+    s.pv_b0 = s.it.b0;
     s.pv_first = kt == 0;
     s.pv_last = last;
   }
   ++s.t;
-  if (last) s.active = false;  // until the item advances after its last PV
-}
-__device__ __forceinline__ void at_stream_after_pv(AtStream& s, const AttnFwdParams& p) {
-  s.pv_pending = false;
-  if (s.pv_last) {
+  if (last) {
     s.idx += 2 * gridDim.x;
     s.t = 0;
     s.active = s.idx < p.items;
@@ -190,14 +193,18 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
           phase ^= 1;
         }
       };
+      // slot of a group = [QK^T of its next step] then [PV its previous step owes]: the next S is in flight while the
+      // softmax of the previous one is still writing P
       while (st[0].active || st[0].pv_pending || st[1].active || st[1].pv_pending) {
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           AtStream& s = st[g];
-          if (s.pv_pending) {
-            ring_load(s.it, 2, s.pv_kt);  // V tile
-            at_stream_after_pv(s, p);
-          }
+          const bool owe = s.pv_pending;
+          const int owe_kt = s.pv_kt;
+          AtItem owe_it;               // the item of the step that owes the PV (s.it may already be the next item)
+          owe_it.h = s.pv_h;
+          owe_it.b0 = s.pv_b0;
+          s.pv_pending = false;
           if (s.active) {
             int kt;
             bool dm, de;
@@ -209,8 +216,9 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
               ++n_q[g];
             }
             ring_load(s.it, 1, kt);  // K tile
-            at_stream_after_s(s);
+            at_stream_after_s(s, p);
           }
+          if (owe) ring_load(owe_it, 2, owe_kt);  // V tile of the step whose PV is owed
         }
       }
     }
@@ -230,29 +238,12 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
         for (int g = 0; g < 2; ++g) {
           AtStream& s = st[g];
           const uint32_t t_s = tmem_base + g * AT_TMEM_GROUP;
-          if (s.pv_pending) {
-            mbar_wait(&p_full[g], n_p[g] & 1);
-            if (s.pv_first && n_o[g] > 0) mbar_wait(&o_free[g], (n_o[g] - 1) & 1);
-            mbar_wait(&kv_full[stage], phase);
-            tc_fence_after();
-            const int kv_valid = p.G == 2 ? 128 : (p.L - s.pv_kt * 128 < 128 ? p.L - s.pv_kt * 128 : 128);
-            const int nkk = (kv_valid + 15) >> 4;
-            const uint32_t sp = smem_u32(p_s + g * AT_P);
-            const uint32_t sv = smem_u32(ring + stage * AT_TILE);
-            for (int kk = 0; kk < nkk; ++kk)
-              umma_bf16(t_s + 128, umma_smem_desc(sp + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
-                        umma_smem_desc(sv + kk * 2048, 8192, 1024), idesc_pv, (s.pv_first && kk == 0) ? 0u : 1u);
-            umma_commit(&pv_done[g]);
-            umma_commit(&kv_empty[stage]);
-            if (++stage == AT_STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-            ++n_p[g];
-            if (s.pv_last) ++n_o[g];
-            at_stream_after_pv(s, p);
-          }
+          const bool owe = s.pv_pending;
+          const int owe_kt = s.pv_kt;
+          const bool owe_first = s.pv_first, owe_last = s.pv_last;
+          s.pv_pending = false;
           if (s.active) {
+            // ---- QK^T of the next step: needs only the S columns back (all rows loaded them), not the P tile
             if (s.t == 0) mbar_wait(&q_full[g], n_q[g] & 1);
             if (n_s[g] > 0) mbar_wait(&s_free[g], (n_s[g] - 1) & 1);
             mbar_wait(&kv_full[stage], phase);
@@ -274,7 +265,29 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
               ++n_q[g];
             }
             ++n_s[g];
-            at_stream_after_s(s);
+            at_stream_after_s(s, p);
+          }
+          if (owe) {
+            // ---- PV owed by the previous step
+            mbar_wait(&p_full[g], n_p[g] & 1);
+            if (owe_first && n_o[g] > 0) mbar_wait(&o_free[g], (n_o[g] - 1) & 1);
+            mbar_wait(&kv_full[stage], phase);
+            tc_fence_after();
+            const int kv_valid = p.G == 2 ? 128 : (p.L - owe_kt * 128 < 128 ? p.L - owe_kt * 128 : 128);
+            const int nkk = (kv_valid + 15) >> 4;
+            const uint32_t sp = smem_u32(p_s + g * AT_P);
+            const uint32_t sv = smem_u32(ring + stage * AT_TILE);
+            for (int kk = 0; kk < nkk; ++kk)
+              umma_bf16(t_s + 128, umma_smem_desc(sp + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+                        umma_smem_desc(sv + kk * 2048, 8192, 1024), idesc_pv, (owe_first && kk == 0) ? 0u : 1u);
+            umma_commit(&pv_done[g]);
+            umma_commit(&kv_empty[stage]);
+            if (++stage == AT_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            ++n_p[g];
+            if (owe_last) ++n_o[g];
           }
         }
       }
@@ -314,22 +327,42 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
         // TMEM reads are software-pipelined: chunk j+1 is requested before the math of chunk j (two register sets,
         // the loop is written two chunks at a time so that the sets are never selected dynamically)
         uint32_t ra[32], rb[32];
-        auto pipelined = [&](auto&& process) {
+        // `release`: this is the step's last sweep over S — the moment the last chunk is in registers the S columns are
+        // handed back to the MMA issuer, so the next QK^T runs while this step's math / P stores are still going on
+        auto hand_back_s = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        };
+        auto pipelined = [&](bool release, auto&& process) {
+#if !AT_PIPELINED_LD
+          // (measured: on this kernel the two-set pipelining costs more in register moves than the overlap returns)
+          for (int j = 0; j < nchunk; ++j) {
+            tmem_ld_32x32_issue(t_row + cbase + j * 32, ra);
+            tmem_ld_wait(ra);
+            if (release && j + 1 == nchunk) hand_back_s();
+            process(ra, j);
+          }
+          (void)rb;
+          return;
+#endif
           tmem_ld_32x32_issue(t_row + cbase, ra);
           tmem_ld_wait(ra);
           for (int j = 0; j < nchunk; j += 2) {
             if (j + 1 < nchunk) tmem_ld_32x32_issue(t_row + cbase + (j + 1) * 32, rb);
+            else if (release) hand_back_s();
             process(ra, j);
             if (j + 1 < nchunk) {
               tmem_ld_wait(rb);
               if (j + 2 < nchunk) tmem_ld_32x32_issue(t_row + cbase + (j + 2) * 32, ra);
+              else if (release) hand_back_s();
               process(rb, j + 1);
               if (j + 2 < nchunk) tmem_ld_wait(ra);
             }
           }
         };
         if (do_max) {
-          pipelined([&](uint32_t (&cur)[32], int j) {
+          pipelined(!do_exp, [&](uint32_t (&cur)[32], int j) {
             if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {  // every key of the chunk visible to every row of the warp
               float m0 = __uint_as_float(cur[0]), m1 = __uint_as_float(cur[1]), m2 = __uint_as_float(cur[2]),
                     m3 = __uint_as_float(cur[3]);
@@ -351,7 +384,7 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
         if (do_exp) {
           if (n_p > 0) mbar_wait(&pv_done[g], (n_p - 1) & 1);  // the previous PV has finished reading the P tile
           const f32x2 sc2 = f2_splat(p.scale_log2), nm2 = f2_splat(-m);
-          pipelined([&](uint32_t (&cur)[32], int j) {
+          pipelined(true, [&](uint32_t (&cur)[32], int j) {
             float v[32];
             f32x2 acc2 = f2_splat(0.f);
             if (__all_sync(0xffffffffu, (j + 1) * 32 <= kmax)) {
@@ -389,11 +422,9 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
           });
           fence_proxy_async_smem();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_free[g]);
-          if (do_exp) mbar_arrive(&p_full[g]);
+        if (do_exp) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[g]);
         }
         ++n_s;
         if (do_exp) ++n_p;
@@ -451,7 +482,13 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
 // dK over K, dV over V) by three TMA stores; the in_proj bias gradient (column sums of dqkv) is accumulated per head
 // in shared memory and flushed with one atomicAdd per column when the CTA's contiguous item range changes head.
 // ===================================================================================================
-constexpr int AT_BWD_SMEM = 2 * 5 * AT_TILE + 2 * AT_P + 192 * 4 + 256 + 1024;
+// Shared-memory plan (bytes): two input stages [Q, K, V, dO] = 128 K, then
+//   G == 2 (L <= 64, two sequences per tile): output staging [dQ, dK, dV] 48 K | P 24 K | dS 24 K — P and dS are block
+//           diagonal, stored as [seq-0 block | 8 K of zeros | seq-1 block] with the two 64-column panels OVERLAPPING on
+//           the zero block (panel stride 8 K instead of 16 K): the input stage is free the moment the output MMAs
+//           retire (tcgen05.commit arrives `in_empty`), the stores drain from their own tiles
+//   G == 1 (64 < L <= 128): P 32 K | dS 32 K, outputs staged over the stage's own Q / K / V tiles
+constexpr int AT_BWD_SMEM = 2 * 4 * AT_TILE + 3 * AT_TILE + 2 * (AT_P - 8192) + 2 * 128 * 4 + 256 + 1024;
 static_assert(AT_BWD_SMEM <= 227 * 1024, "attention bwd smem budget");
 
 struct AttnBwdParams {
@@ -489,11 +526,15 @@ __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* in_s = smem;                     // [2 stages][Q, K, V, dO, O]
-  uint8_t* p_s = in_s + 2 * 5 * AT_TILE;    // P tile
-  uint8_t* ds_s = p_s + AT_P;               // dS tile
-  float* bias_s = reinterpret_cast<float*>(ds_s + AT_P);  // [3][64] per-head bias-gradient accumulators
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 192);
+  const bool two = p.G == 2;
+  const int pan = two ? 8192 : 16384;       // stride between the two 64-column panels of P / dS
+  const int pbytes = two ? AT_P - 8192 : AT_P;
+  uint8_t* in_s = smem;                     // [2 stages][Q, K, V, dO]
+  uint8_t* out_s = in_s + 2 * 4 * AT_TILE;  // G == 2 only: [dQ, dK, dV] staging
+  uint8_t* p_s = two ? out_s + 3 * AT_TILE : out_s;  // P tile
+  uint8_t* ds_s = p_s + pbytes;             // dS tile
+  float* xch = reinterpret_cast<float*>(smem + 2 * 4 * AT_TILE + 3 * AT_TILE + 2 * (AT_P - 8192));  // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 256);
   uint64_t* in_full = bars;       // [2]
   uint64_t* in_empty = bars + 2;  // [2]
   uint64_t* sdp_full = bars + 4;  // S and dP in TMEM
@@ -502,7 +543,8 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   uint64_t* acc_free = bars + 7;  // TMEM read by the epilogue (8 warps)
   uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> warps 2 and 3
   uint64_t* sums_done = bars + 9; // warp 2 -> warp 3
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* stg_free = bars + 10; // G == 2: the staging tiles have been read by the stores and the sums (warp 3)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -526,6 +568,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     mbar_init(acc_free, 8);
     mbar_init(staged, 8);
     mbar_init(sums_done, 1);
+    mbar_init(stg_free, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -533,12 +576,11 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     tmem_relinquish();
   }
   if (warp >= 4) {
-    // P / dS start as zeros and are never used as staging: the off-diagonal blocks (two sequences per tile) and
-    // the key columns no row writes stay zero for the whole kernel
+    // P / dS start as zeros and are never used as staging: the zero block between the two sequences' blocks (G == 2)
+    // and the key columns no row writes stay zero for the whole kernel
     const int t = threadIdx.x - 128;  // 0..255
     uint4* z = reinterpret_cast<uint4*>(p_s);
-    for (int i = t; i < 2 * AT_P / 16; i += 256) z[i] = make_uint4(0, 0, 0, 0);
-    if (t < 192) bias_s[t] = 0.f;
+    for (int i = t; i < 2 * pbytes / 16; i += 256) z[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
   }
   tc_fence_before();
@@ -554,13 +596,12 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         const int n = idx - i0, stage = n & 1;
         const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
         if (n >= 2) mbar_wait(&in_empty[stage], ((n >> 1) - 1) & 1);
-        uint8_t* st = in_s + stage * 5 * AT_TILE;
-        mbar_expect_tx(&in_full[stage], 5 * AT_TILE);
+        uint8_t* st = in_s + stage * 4 * AT_TILE;
+        mbar_expect_tx(&in_full[stage], 4 * AT_TILE);
         tma_load_3d(st, &tm.qkv, &in_full[stage], h * 64, 0, b0);
         tma_load_3d(st + AT_TILE, &tm.qkv, &in_full[stage], p.D + h * 64, 0, b0);
         tma_load_3d(st + 2 * AT_TILE, &tm.qkv, &in_full[stage], 2 * p.D + h * 64, 0, b0);
         tma_load_3d(st + 3 * AT_TILE, &tm.dout, &in_full[stage], h * 64, 0, b0);
-        tma_load_3d(st + 4 * AT_TILE, &tm.out, &in_full[stage], h * 64, 0, b0);  // O: D = rowsum(dO o O)
       }
     }
   } else if (warp == 1) {
@@ -574,7 +615,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       // item n's P / dS are in shared memory), so the softmax-gradient warps find them ready after item n's epilogue
       auto issue_sdp = [&](int n) {
         const int stage = n & 1;
-        const uint32_t sq = smem_u32(in_s + stage * 5 * AT_TILE), sk = sq + AT_TILE, sv = sq + 2 * AT_TILE, sdo = sq + 3 * AT_TILE;
+        const uint32_t sq = smem_u32(in_s + stage * 4 * AT_TILE), sk = sq + AT_TILE, sv = sq + 2 * AT_TILE, sdo = sq + 3 * AT_TILE;
         mbar_wait(&in_full[stage], (n >> 1) & 1);
         tc_fence_after();
 #pragma unroll
@@ -589,20 +630,21 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       if (i0 < i1) issue_sdp(0);
       for (int idx = i0; idx < i1; ++idx) {
         const int n = idx - i0, stage = n & 1;
-        const uint32_t sq = smem_u32(in_s + stage * 5 * AT_TILE), sk = sq + AT_TILE, sdo = sq + 3 * AT_TILE;
+        const uint32_t sq = smem_u32(in_s + stage * 4 * AT_TILE), sk = sq + AT_TILE, sdo = sq + 3 * AT_TILE;
         mbar_wait(pds_full, n & 1);
         if (n > 0) mbar_wait(acc_free, (n - 1) & 1);  // the previous item's dV / dK / dQ have been read out of TMEM
         tc_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dV[key, d] = sum_q P[q, key] dO[q, d]
-          umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, 16384, 1024), umma_smem_desc(sdo + kk * 2048, 8192, 1024),
+          umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, pan, 1024), umma_smem_desc(sdo + kk * 2048, 8192, 1024),
                     id_t, kk > 0);
         for (int kk = 0; kk < nk; ++kk)  // dK[key, d] = sum_q dS[q, key] Q[q, d]
-          umma_bf16(tmem_base + 320, umma_smem_desc(sds + kk * 2048, 16384, 1024), umma_smem_desc(sq + kk * 2048, 8192, 1024),
+          umma_bf16(tmem_base + 320, umma_smem_desc(sds + kk * 2048, pan, 1024), umma_smem_desc(sq + kk * 2048, 8192, 1024),
                     id_t, kk > 0);
         for (int kk = 0; kk < nk; ++kk)  // dQ[q, d] = sum_key dS[q, key] K[key, d]
-          umma_bf16(tmem_base + 384, umma_smem_desc(sds + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024),
+          umma_bf16(tmem_base + 384, umma_smem_desc(sds + (kk >> 2) * pan + (kk & 3) * 32, 16, 1024),
                     umma_smem_desc(sk + kk * 2048, 8192, 1024), id_q, kk > 0);
         umma_commit(out_full);
+        if (two) umma_commit(&in_empty[stage]);  // nothing reads the stage's tiles any more: the producer may refill it
         if (idx + 1 < i1) issue_sdp(n + 1);
       }
     }
@@ -626,7 +668,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     for (int idx = i0; idx < i1; ++idx) {
       const int n = idx - i0, stage = n & 1;
       const int h = idx / p.nb, b0 = (idx % p.nb) * p.G;
-      uint8_t* st = in_s + stage * 5 * AT_TILE;
+      uint8_t* st = two ? out_s : in_s + stage * 4 * AT_TILE;  // where the epilogue staged dQ | dK | dV
       if (h != cur_h) {
         flush();
         cur_h = h;
@@ -657,9 +699,9 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       if (warp == 2) {
         if (lane == 0) mbar_arrive(sums_done);  // the dQ tile has been summed
       } else if (lane == 0) {
-        tma_store_wait_read<0>();       // the stage's tiles have been read by the stores ...
-        mbar_wait(sums_done, n & 1);    // ... and by warp 2: the producer may refill them
-        mbar_arrive(&in_empty[stage]);
+        tma_store_wait_read<0>();       // the staged tiles have been read by the stores ...
+        mbar_wait(sums_done, n & 1);    // ... and by warp 2: they may be overwritten
+        mbar_arrive(two ? stg_free : &in_empty[stage]);
       }
       __syncwarp();
     }
@@ -677,80 +719,96 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     if (p.causal) kmax = qi + 1 < kmax ? qi + 1 : kmax;
     const int nchunk = p.G == 2 ? 2 : (p.L + 31) >> 5;   // 32-column chunks holding keys of this row's block
     const int per = p.G == 2 ? 1 : 2;                    // chunks per column half
-    // per-item row constants (log-sum-exp, D = rowsum(dO o O)); computed one item AHEAD, in the window where the
-    // warps would otherwise only wait for the output MMAs
-    auto row_consts = [&](int idx, bool& valid, float& lse2, float& drow) {
-      const int n = idx - i0, stage = n & 1;
+    // Row constants: the log-sum-exp is fetched one item AHEAD; D = rowsum(dO o O) is never read from memory — with
+    // the whole key range of a row in one tile it equals sum_key P dP (O = P V), which the two column halves of a row
+    // accumulate in fp32 from the accumulators they hold anyway and exchange through shared memory.
+    auto row_lse = [&](int idx, bool& valid) -> float {
       const int h = idx / p.nb, b = (idx % p.nb) * p.G + seq;
-      const uint8_t* st = in_s + stage * 5 * AT_TILE;
       valid = qi < p.L && b < p.B;
-      lse2 = 0.f;
-      drow = 0.f;
-      float lse_v = 0.f;
-      if (valid) lse_v = __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi);
-      mbar_wait(&in_full[stage], (n >> 1) & 1);
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float a[8], d8[8];
-          const int sw = (c ^ (r & 7)) << 4;
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 4 * AT_TILE + r * 128 + sw), a);
-          unpack_bf16x8(*reinterpret_cast<const uint4*>(st + 3 * AT_TILE + r * 128 + sw), d8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) drow = fmaf(a[i], d8[i], drow);
-        }
-        lse2 = lse_v * kLog2eAt;
-      }
+      return valid ? __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt : 0.f;
     };
     bool valid = false, nvalid_row = false;
-    float lse2 = 0.f, drow = 0.f, nlse2 = 0.f, ndrow = 0.f;
-    if (i0 < i1) row_consts(i0, valid, lse2, drow);
+    float lse2 = 0.f, nlse2 = 0.f;
+    if (i0 < i1) lse2 = row_lse(i0, valid);
+    const int prow = two ? (r & 63) : r;                 // row inside the row's own P / dS block
+    const int pblk = two ? seq * 16384 : 0;              // G == 2: [seq-0 block | zeros | seq-1 block]
     for (int idx = i0; idx < i1; ++idx) {
       const int n = idx - i0, stage = n & 1;
-      uint8_t* st = in_s + stage * 5 * AT_TILE;
+      uint8_t* st = two ? out_s : in_s + stage * 4 * AT_TILE;
+      if (idx + 1 < i1) nlse2 = row_lse(idx + 1, nvalid_row);
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
-      for (int jj = 0; jj < per; ++jj) {
+      // pass 1: P (stored, and kept as packed bf16) and this half's share of D
+      uint32_t pk[2][16];
+      float part = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
         const int j = half * per + jj;
-        if (j >= nchunk) break;
-        float s[32], dp[32];
-        tmem_ld_32x32(t_row + cbase + j * 32, s);
-        tmem_ld_32x32(t_row + 128 + cbase + j * 32, dp);
+        if (jj < per && j < nchunk) {
+          float sv[32], dp[32];
+          tmem_ld_32x32(t_row + cbase + j * 32, sv);
+          tmem_ld_32x32(t_row + 128 + cbase + j * 32, dp);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool ok = valid && (j * 32 + i < kmax);
-          const float pr = ok ? ex2_approx(fmaf(s[i], p.scale_log2, -lse2)) : 0.f;
-          s[i] = pr;
-          dp[i] = pr * (dp[i] - drow) * p.scale;
-        }
-        const int c0 = cbase + j * 32;
-        const int off = (c0 >> 6) * 16384 + r * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          float t8[8], u8[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            t8[i] = s[q4 * 8 + i];
-            u8[i] = dp[q4 * 8 + i];
+          for (int i = 0; i < 32; ++i) {
+            const bool ok = valid && (j * 32 + i < kmax);
+            const float pr = ok ? ex2_approx(fmaf(sv[i], p.scale_log2, -lse2)) : 0.f;
+            sv[i] = pr;
+            part = fmaf(pr, dp[i], part);
           }
-          const int ch = ((((c0 & 63) >> 3) + q4) ^ (r & 7)) << 4;
-          *reinterpret_cast<uint4*>(p_s + off + ch) = pack_bf16x8(t8);
-          *reinterpret_cast<uint4*>(ds_s + off + ch) = pack_bf16x8(u8);
+          const int c0 = j * 32;  // first key of the chunk inside the row's block
+          uint8_t* rowp = p_s + pblk + (two ? 0 : (c0 >> 6) * 16384) + prow * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float t8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = sv[q4 * 8 + i];
+            const uint4 w = pack_bf16x8(t8);
+            pk[jj][q4 * 4] = w.x;
+            pk[jj][q4 * 4 + 1] = w.y;
+            pk[jj][q4 * 4 + 2] = w.z;
+            pk[jj][q4 * 4 + 3] = w.w;
+            *reinterpret_cast<uint4*>(rowp + (((((c0 & 63) >> 3) + q4) ^ (r & 7)) << 4)) = w;
+          }
+        }
+      }
+      xch[half * 128 + r] = part;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the row's other column half (warp +-4)
+      const float drow = part + xch[(1 - half) * 128 + r];
+      // pass 2: dS = P (dP - D) scale
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = half * per + jj;
+        if (jj < per && j < nchunk) {
+          float dp[32];
+          tmem_ld_32x32(t_row + 128 + cbase + j * 32, dp);
+          const int c0 = j * 32;
+          uint8_t* rowp = ds_s + pblk + (two ? 0 : (c0 >> 6) * 16384) + prow * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float u8[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t w = pk[jj][q4 * 4 + i];
+              u8[2 * i] = __uint_as_float(w << 16) * (dp[q4 * 8 + 2 * i] - drow) * p.scale;
+              u8[2 * i + 1] = __uint_as_float(w & 0xffff0000u) * (dp[q4 * 8 + 2 * i + 1] - drow) * p.scale;
+            }
+            *reinterpret_cast<uint4*>(rowp + (((((c0 & 63) >> 3) + q4) ^ (r & 7)) << 4)) = pack_bf16x8(u8);
+          }
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      if (idx + 1 < i1) row_consts(idx + 1, nvalid_row, nlse2, ndrow);  // overlaps the dV / dK / dQ MMAs
-      // ---- epilogue: dQ | dK | dV columns [half*32, half*32+32) of row r -> bf16 -> the stage's Q | K | V tile
+      // ---- epilogue: dQ | dK | dV columns [half*32, half*32+32) of row r -> bf16 -> staging tile
       mbar_wait(out_full, n & 1);
+      if (two && n > 0) mbar_wait(stg_free, (n - 1) & 1);  // the previous item's stores / sums are done with the tiles
       tc_fence_after();
 #pragma unroll 1
-      for (int part = 0; part < 3; ++part) {  // part 0: dQ (TMEM 384, over Q), 1: dK (320, over K), 2: dV (256, over V)
+      for (int part_i = 0; part_i < 3; ++part_i) {  // 0: dQ (TMEM 384, Q tile), 1: dK (320, K tile), 2: dV (256, V tile)
         float v[32];
-        tmem_ld_32x32(t_row + 384 - part * 64 + half * 32, v);
-        uint8_t* dst = st + part * AT_TILE + r * 128;
+        tmem_ld_32x32(t_row + 384 - part_i * 64 + half * 32, v);
+        uint8_t* dst = st + part_i * AT_TILE + r * 128;
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
           float t8[8];
@@ -768,7 +826,6 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       }
       valid = nvalid_row;
       lse2 = nlse2;
-      drow = ndrow;
     }
   }
 
