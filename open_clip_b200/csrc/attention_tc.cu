@@ -544,7 +544,9 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> warps 2 and 3
   uint64_t* sums_done = bars + 9; // warp 2 -> warp 3
   uint64_t* stg_free = bars + 10; // G == 2: the staging tiles have been read by the stores and the sums (warp 3)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* p_full = bars + 11;   // P in shared memory (8 warps): dV's MMAs start while dS is still being computed
+  uint64_t* dv_full = bars + 12;  // dV in TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -569,6 +571,8 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     mbar_init(staged, 8);
     mbar_init(sums_done, 1);
     mbar_init(stg_free, 1);
+    mbar_init(p_full, 8);
+    mbar_init(dv_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -631,12 +635,15 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       for (int idx = i0; idx < i1; ++idx) {
         const int n = idx - i0, stage = n & 1;
         const uint32_t sq = smem_u32(in_s + stage * 4 * AT_TILE), sk = sq + AT_TILE, sdo = sq + 3 * AT_TILE;
-        mbar_wait(pds_full, n & 1);
+        mbar_wait(p_full, n & 1);
         if (n > 0) mbar_wait(acc_free, (n - 1) & 1);  // the previous item's dV / dK / dQ have been read out of TMEM
         tc_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dV[key, d] = sum_q P[q, key] dO[q, d]
           umma_bf16(tmem_base + 256, umma_smem_desc(sp + kk * 2048, pan, 1024), umma_smem_desc(sdo + kk * 2048, 8192, 1024),
                     id_t, kk > 0);
+        umma_commit(dv_full);  // drained by the epilogue warps while dK / dQ are still in the pipe
+        mbar_wait(pds_full, n & 1);
+        tc_fence_after();
         for (int kk = 0; kk < nk; ++kk)  // dK[key, d] = sum_q dS[q, key] Q[q, d]
           umma_bf16(tmem_base + 320, umma_smem_desc(sds + kk * 2048, pan, 1024), umma_smem_desc(sq + kk * 2048, 8192, 1024),
                     id_t, kk > 0);
@@ -722,22 +729,25 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     // Row constants: the log-sum-exp is fetched one item AHEAD; D = rowsum(dO o O) is never read from memory — with
     // the whole key range of a row in one tile it equals sum_key P dP (O = P V), which the two column halves of a row
     // accumulate in fp32 from the accumulators they hold anyway and exchange through shared memory.
+    // (returns the raw value: the conversion to log2 units happens where it is consumed, one item later, so the load
+    // has a whole item to land)
     auto row_lse = [&](int idx, bool& valid) -> float {
       const int h = idx / p.nb, b = (idx % p.nb) * p.G + seq;
       valid = qi < p.L && b < p.B;
-      return valid ? __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) * kLog2eAt : 0.f;
+      return valid ? __ldg(p.lse + (static_cast<int64_t>(b) * p.H + h) * p.L + qi) : 0.f;
     };
     bool valid = false, nvalid_row = false;
-    float lse2 = 0.f, nlse2 = 0.f;
-    if (i0 < i1) lse2 = row_lse(i0, valid);
+    float lse_raw = 0.f, nlse_raw = 0.f;
+    if (i0 < i1) lse_raw = row_lse(i0, valid);
     const int prow = two ? (r & 63) : r;                 // row inside the row's own P / dS block
     const int pblk = two ? seq * 16384 : 0;              // G == 2: [seq-0 block | zeros | seq-1 block]
     for (int idx = i0; idx < i1; ++idx) {
       const int n = idx - i0, stage = n & 1;
       uint8_t* st = two ? out_s : in_s + stage * 4 * AT_TILE;
-      if (idx + 1 < i1) nlse2 = row_lse(idx + 1, nvalid_row);
+      if (idx + 1 < i1) nlse_raw = row_lse(idx + 1, nvalid_row);
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
+      const float lse2 = lse_raw * kLog2eAt;
       // pass 1: P (stored, and kept as packed bf16) and this half's share of D
       uint32_t pk[2][16];
       float part = 0.f;
@@ -772,6 +782,10 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         }
       }
       xch[half * 128 + r] = part;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");  // the row's other column half (warp +-4)
       const float drow = part + xch[(1 - half) * 128 + r];
       // pass 2: dS = P (dP - D) scale
@@ -800,12 +814,18 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // ---- epilogue: dQ | dK | dV columns [half*32, half*32+32) of row r -> bf16 -> staging tile
-      mbar_wait(out_full, n & 1);
+      // ---- epilogue: dV | dK | dQ columns [half*32, half*32+32) of row r -> bf16 -> staging tile; dV first (its MMAs
+      // ran during pass 2), dK / dQ when theirs retire
+      mbar_wait(dv_full, n & 1);
       if (two && n > 0) mbar_wait(stg_free, (n - 1) & 1);  // the previous item's stores / sums are done with the tiles
       tc_fence_after();
 #pragma unroll 1
-      for (int part_i = 0; part_i < 3; ++part_i) {  // 0: dQ (TMEM 384, Q tile), 1: dK (320, K tile), 2: dV (256, V tile)
+      for (int k3 = 0; k3 < 3; ++k3) {  // tile 2: dV (TMEM 256, V tile), 1: dK (320, K tile), 0: dQ (384, Q tile)
+        const int part_i = 2 - k3;
+        if (k3 == 1) {
+          mbar_wait(out_full, n & 1);
+          tc_fence_after();
+        }
         float v[32];
         tmem_ld_32x32(t_row + 384 - part_i * 64 + half * 32, v);
         uint8_t* dst = st + part_i * AT_TILE + r * 128;
@@ -825,7 +845,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         mbar_arrive(staged);
       }
       valid = nvalid_row;
-      lse2 = nlse2;
+      lse_raw = nlse_raw;
     }
   }
 
