@@ -143,8 +143,8 @@ def logits_gemm_roofline(sig_time, sig_count, peak_tflops):
     if n == 0 or ms <= 0:
         return None
     tf = sum(2.0 * s[0] * s[1] * s[2] * sig_count[s] for s in lse_sigs) / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_peer_kernel<128,LSE> (both directions in one launch: peer-read column "
-                                        "tiles stationary in smem + online row LSE) + lse_combine",
+    return {"bound": "tensor", "kernel": "gemm_peer_kernel<BN,LSE> (BN = 256 for E <= 512, else 128; both directions in one "
+                                        "launch: column tiles stationary in smem + online row LSE) + lse_combine",
             "achieved": tf, "peak": peak_tflops, "unit": "TFLOP/s", "frac": tf / peak_tflops, "launches_timed": n,
             "avg_launch_ms": ms / n, "shape_mnk": [list(s[:3]) for s in lse_sigs]}
 
@@ -372,7 +372,10 @@ def main():
     ops.PROFILE_KEY = "all"
     ops.PROFILE_EVENTS.clear()
     ops.LAUNCHES = 0
+    ops.stage_timing(True)   # library-side events between the gather / GEMM / combine kernels of the fused loss forward
     ms_step = timed(resident, args.steps)
+    stage = ops.stage_times()
+    ops.stage_timing(False)
     launches = ops.LAUNCHES // max(args.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
     sig_time, sig_count = {}, {}
@@ -453,6 +456,11 @@ def main():
         except (OSError, ValueError, KeyError):
             pass
         logits_roofline = logits_gemm_roofline(sig_time, sig_count, peaks["bf16_sustained"])
+        if logits_roofline is not None and stage[0] > 0 and not args.siglip:
+            # the launch split into its kernels: peer gather (NVLink reads, W > 1) | tcgen05 GEMM + online LSE | combine
+            flops = 2.0 * 2 * B * world * B * model.embed_dim
+            logits_roofline["stages_ms"] = {"calls": stage[0], "peer_gather": stage[1], "gemm": stage[2], "combine": stage[3]}
+            logits_roofline["gemm_kernel_frac"] = flops / (stage[2] * 1e-3) / 1e12 / peaks["bf16_sustained"] if stage[2] > 0 else None
         out = {
             "metric": "image-text pairs/sec (full train step)", "value": pairs_per_s, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -478,6 +486,13 @@ def main():
                               "frac": pairs_per_s / world * step_gflop / 1e3 / peaks["bf16_sustained"],
                               "flops_per_pair": step_gflop * 1e9},
             "roofline_logits_gemm": logits_roofline,
+            # every GEMM signature of the timed region, largest total first (same live CUDA-event timings)
+            "roofline_gemm_signatures": [
+                {"epilogue": epi_names[s[3]], "m": s[0], "n": s[1], "k": s[2], "mn_major": bool(s[4]),
+                 "launches_per_step": sig_count[s] / args.steps, "avg_launch_ms": sig_time[s] / sig_count[s],
+                 "share_of_step": (sig_time[s] / args.steps) / ms_step,
+                 "frac": 2.0 * s[0] * s[1] * s[2] / (sig_time[s] / sig_count[s] * 1e-3) / 1e12 / peaks["bf16_sustained"]}
+                for s in sorted(sig_time, key=sig_time.get, reverse=True)[:12]],
             "gpu_launches": launches,
             "clocks": clocks,
             "hbm_peak_allocated_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),

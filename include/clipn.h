@@ -223,6 +223,11 @@ int32_t clipn_peer_gemm_tile_n(int32_t world, int32_t b, int32_t e);
 int clipn_peer_gather(const void* const* txt_cols, const void* const* img_cols, int32_t world, int32_t b, int32_t e,
                       void* gather_txt, void* gather_img, clipn_stream_t stream);
 int64_t clipn_clip_fwd_fused_workspace(int32_t world, int32_t b, int32_t e);
+/* Measurement aid (bench.py): with clipn_stage_timing(1), every clipn_clip_fwd_fused call records CUDA events on its
+ * stream between the peer gather, the GEMM and the combine kernel (up to 64 calls); clipn_stage_times writes the mean
+ * milliseconds of the three stages to out[3] and returns the number of calls averaged.  Off by default. */
+int clipn_stage_timing(int32_t enable);
+int32_t clipn_stage_times(float* out);
 int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, const void* const* txt_cols,
                          const void* const* img_cols, int32_t world, int32_t rank, int32_t b, int32_t e, float scale,
                          const float* scale_dev, void* gather_txt, void* gather_img, float* lse, float* loss_acc,

@@ -75,6 +75,8 @@ SIGNATURES = {
     "clipn_peer_gemm_tile_n": (_I32, [_I32, _I32, _I32]),
     "clipn_peer_gather": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _P, _P, _P]),
     "clipn_clip_fwd_fused_workspace": (C.c_int64, [_I32, _I32, _I32]),
+    "clipn_stage_timing": (C.c_int, [_I32]),
+    "clipn_stage_times": (_I32, [C.POINTER(C.c_float)]),
     "clipn_clip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32, _F,
                                        _P, _P, _P, _P, _P, _P, _P]),
     "clipn_siglip_fwd_fused": (C.c_int, [_P, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _I32, _I32, _I32, _I32,

@@ -17,38 +17,55 @@ namespace clipn {
 
 // combine per-slab (max, sum) partials into the row LSE: lse[m] = log sum_n exp(s[m,n]); optionally accumulate
 // loss_acc += loss_scale * sum_m (lse[m] - pos[m])   (the cross-entropy value of this direction)
+// Block = 32 consecutive rows (lanes: coalesced [slab][row] reads) x 8 slab subsets (warps); the subsets are merged
+// through shared memory.  (One thread per row walking all slabs serially took 22 us at 64 slabs — latency-bound.)
 __global__ void __launch_bounds__(256) lse_combine_kernel(const float* __restrict__ part_max,
                                                           const float* __restrict__ part_sum,
                                                           const float* __restrict__ pos, float* __restrict__ lse,
                                                           float* __restrict__ loss_acc, float loss_scale, int m,
                                                           int slabs, int64_t dir_stride_part, int64_t dir_stride_vec) {
+  __shared__ float red[8][32];
   const int dir = blockIdx.y;
   part_max += dir * dir_stride_part;
   part_sum += dir * dir_stride_part;
   lse += dir * dir_stride_vec;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  float local = 0.f;
-  if (row < m) {
-    float mx = -INFINITY;
-    for (int s = 0; s < slabs; ++s) mx = fmaxf(mx, part_max[static_cast<int64_t>(s) * m + row]);
-    float sum = 0.f;
-    for (int s = 0; s < slabs; ++s) {
-      const float pm = part_max[static_cast<int64_t>(s) * m + row];
-      if (pm != -INFINITY) sum += part_sum[static_cast<int64_t>(s) * m + row] * expf(pm - mx);  // precise: the
-    }                                                      // backward differentiates through exp(s - lse)
-    const float l = mx + logf(sum);
-    lse[row] = l;
-    if (pos != nullptr) local = l - pos[dir * dir_stride_vec + row];
+  const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+  const int row = blockIdx.x * 32 + lane;
+  const bool live = row < m;
+  float mx = -INFINITY;
+  if (live) {
+#pragma unroll 4
+    for (int s = sub; s < slabs; s += 8) mx = fmaxf(mx, part_max[static_cast<int64_t>(s) * m + row]);
   }
-  if (loss_acc != nullptr) {
-    __shared__ float red[8];
-    local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  red[sub][lane] = mx;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mx = fmaxf(mx, red[i][lane]);
+  __syncthreads();
+  float sum = 0.f;
+  if (live) {
+#pragma unroll 4
+    for (int s = sub; s < slabs; s += 8) {
+      const float pm = part_max[static_cast<int64_t>(s) * m + row];
+      const float ps = part_sum[static_cast<int64_t>(s) * m + row];
+      if (pm != -INFINITY) sum += ps * expf(pm - mx);  // precise: the backward differentiates through exp(s - lse)
+    }
+  }
+  red[sub][lane] = sum;
+  __syncthreads();
+  if (sub == 0) {
+    float local = 0.f;
+    if (live) {
       float t = 0.f;
-      for (int i = 0; i < 8; ++i) t += red[i];
-      atomicAdd(loss_acc, t * loss_scale);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t += red[i][lane];
+      const float l = mx + logf(t);
+      lse[row] = l;
+      if (pos != nullptr) local = l - pos[dir * dir_stride_vec + row];
+    }
+    if (loss_acc != nullptr) {
+      local = warp_sum(local);
+      if (lane == 0) atomicAdd(loss_acc, local * loss_scale);
     }
   }
 }
@@ -103,6 +120,52 @@ static bool peer_direct() {
     return e != nullptr && e[0] == '1';
   }();
   return on;
+}
+
+// Opt-in stage timing of the fused forward (bench.py / tools: clipn_stage_timing(1)): CUDA events on the launching
+// stream between the gather, the GEMM and the combine kernel of each call; read back (averaged) by
+// clipn_stage_times.  Off by default: no events are recorded.
+namespace {
+constexpr int kStageRing = 64;
+struct StageTimer {
+  bool on = false;
+  int calls = 0;
+  cudaEvent_t ev[kStageRing][4] = {};
+  bool made = false;
+};
+StageTimer g_stage;
+inline void stage_mark(int k, cudaStream_t stream) {
+  if (!g_stage.on || g_stage.calls >= kStageRing) return;
+  if (!g_stage.made) {
+    for (auto& q : g_stage.ev)
+      for (auto& e : q) cudaEventCreate(&e);
+    g_stage.made = true;
+  }
+  cudaEventRecord(g_stage.ev[g_stage.calls][k], stream);
+  if (k == 3) ++g_stage.calls;
+}
+}  // namespace
+
+extern "C" int clipn_stage_timing(int32_t enable) {
+  g_stage.on = enable != 0;
+  g_stage.calls = 0;
+  return CLIPN_OK;
+}
+
+// out[0..2] = mean milliseconds of (gather, GEMM, combine) over the calls recorded since clipn_stage_timing(1);
+// returns the number of calls averaged (synchronises on the last event)
+extern "C" int32_t clipn_stage_times(float* out) {
+  const int n = g_stage.calls;
+  out[0] = out[1] = out[2] = 0.f;
+  if (n == 0) return 0;
+  cudaEventSynchronize(g_stage.ev[n - 1][3]);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, g_stage.ev[i][k], g_stage.ev[i][k + 1]);
+      out[k] += ms / n;
+    }
+  return n;
 }
 
 // gather every rank's columns into the local copies; afterwards the GEMM sees ONE local [W*B, E] operand per direction
@@ -180,6 +243,7 @@ extern "C" int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, 
   memset(&d, 0, sizeof(d));
   d.rows[0] = img_rows; d.rows[1] = txt_rows;
   d.dirs = 2; d.m = b; d.e = e;
+  stage_mark(0, static_cast<cudaStream_t>(stream));
   if (world > 1 && !direct) {
     int rcg = gather_columns(txt_cols, img_cols, world, b, e, gather_txt, gather_img, static_cast<cudaStream_t>(stream));
     if (rcg) return rcg;
@@ -198,12 +262,15 @@ extern "C" int clipn_clip_fwd_fused(const void* img_rows, const void* txt_rows, 
     d.part_sum[dir] = workspace + 2 * part + dir * part;
     d.pos[dir] = pos + dir * static_cast<int64_t>(b);
   }
+  stage_mark(1, static_cast<cudaStream_t>(stream));
   int rc = peer_gemm_launch(d, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
-  dim3 grid((b + 255) / 256, 2);
+  stage_mark(2, static_cast<cudaStream_t>(stream));
+  dim3 grid((b + 31) / 32, 2);
   lse_combine_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(workspace, workspace + 2 * part, pos, lse,
                                                                          loss_acc, 1.0f / (2.0f * b), b, slabs, part, b);
   CLIPN_CHECK_CUDA(cudaGetLastError());
+  stage_mark(3, static_cast<cudaStream_t>(stream));
   return CLIPN_OK;
 }
 
@@ -270,7 +337,7 @@ extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols
   const void* bp[1] = {feats_cols};
   int rc = gemm_launch(d, bp, 1, 0, false, static_cast<cudaStream_t>(stream));
   if (rc) return rc;
-  lse_combine_kernel<<<dim3((m + 255) / 256, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  lse_combine_kernel<<<dim3((m + 31) / 32, 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d.part_max, d.part_sum, nullptr, lse, nullptr, 0.f, m, slabs, 0, 0);
   CLIPN_CHECK_CUDA(cudaGetLastError());
   return CLIPN_OK;

@@ -306,6 +306,18 @@ def _profiled(sig):
     return _Ctx()
 
 
+def stage_timing(enable: bool) -> None:
+    """Measurement aid: record CUDA events between the gather / GEMM / combine stages of every fused ClipLoss forward."""
+    _call(L.lib().clipn_stage_timing(1 if enable else 0))
+
+
+def stage_times():
+    """(calls, gather_ms, gemm_ms, combine_ms): mean stage times since stage_timing(True)."""
+    buf = (C.c_float * 3)()
+    n = L.lib().clipn_stage_times(buf)
+    return int(n), float(buf[0]), float(buf[1]), float(buf[2])
+
+
 def clip_fwd_fused(img: torch.Tensor, txt: torch.Tensor, txt_ptrs: Sequence[int], img_ptrs: Sequence[int], rank: int,
                    scale: torch.Tensor, gather_txt: Optional[torch.Tensor], gather_img: Optional[torch.Tensor]):
     """Both directions of the ClipLoss forward in one launch (+ a tiny combine kernel): returns lse [2, B] (image rows,

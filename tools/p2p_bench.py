@@ -66,6 +66,32 @@ def main():
     big_i, big_t = g.all_img, g.all_txt
     us = timeit(lambda: (ops.clip_lse_fwd(img, big_t, scale, rank * B), ops.clip_lse_fwd(txt, big_i, scale, rank * B)), sync)
     print(f"[rank {rank}] generic lse fwd x2 on the local gathered operands: {us:8.1f} us")
+    # ---- the same call after ~60 ms without any NVLink traffic (as in a training step: the towers run in between) ----
+    # GPU kept busy by local GEMMs so the host runs ahead; stage times from the library's own events.
+    a = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    w = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)
+    tiny_t, tiny_i = torch.empty(world * 8, E, dtype=torch.bfloat16, device=dev), torch.empty(world * 8, E, dtype=torch.bfloat16, device=dev)
+    for warm in (False, True):
+        tot = []
+        ops.stage_timing(True)
+        for k in range(6):
+            for _ in range(80):
+                torch.mm(a, w)
+            g.publish(img, txt)
+            if warm:   # a 8-row peer read ahead of the real one: does waking the links earlier help?
+                ops.peer_gather(txt_ptrs, img_ptrs, 8, E, tiny_t, tiny_i)
+                torch.mm(a, w)
+            _, _, ip, tp = g.publish(img, txt)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.clip_fwd_fused(img, txt, tp, ip, rank, scale, g.all_txt, g.all_img)
+            e1.record()
+            torch.cuda.synchronize()
+            tot.append(e0.elapsed_time(e1) * 1e3)
+        n, tg, tm, tc = ops.stage_times()
+        ops.stage_timing(False)
+        print(f"[rank {rank}] fused forward after 60 ms of link idle (warm-up read {warm}): total {sorted(tot)[len(tot) // 2]:.1f} us "
+              f"(median of {len(tot)}); stages over {n} calls: gather {tg * 1e3:.1f} GEMM {tm * 1e3:.1f} combine {tc * 1e3:.1f} us")
     dist.destroy_process_group()
 
 
