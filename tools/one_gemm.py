@@ -22,6 +22,17 @@ for _ in range(3):
     elif which == "wgrad":     # split-K weight gradient (both operands MN-major, TMA reduce-add)
         gw = torch.zeros(4 * d, d, device="cuda")
         ops.gemm(x4, x, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=gw, splits=ops.wgrad_splits(4 * d, d, M))
+    elif which == "wgradqkv":  # in_proj weight gradient at the benchmarked size: [2304, 768] = dqkv^T x, K = 204800
+        Mq = 204800
+        if _ == 0:
+            xq = torch.randn(Mq, d, device="cuda").to(bf)
+            dq = torch.randn(Mq, 3 * d, device="cuda").to(bf)
+        gw = torch.zeros(3 * d, d, device="cuda")
+        ops.gemm(dq, xq, a_mn=True, b_mn=True, epilogue=L.EPI_ACCUM_F32, out=gw, splits=ops.wgrad_splits(3 * d, d, Mq))
+    elif which == "qkv":       # in_proj forward (plain store epilogue), K = 768
+        w3 = (torch.randn(3 * d, d, device="cuda") * 0.02).to(bf)
+        o3 = torch.empty(M, 3 * d, device="cuda", dtype=bf)
+        ops.gemm(x, w3, out=o3)
     elif which == "resid":     # out_proj / c_proj forward with the residual add
         b1 = torch.zeros(d, device="cuda", dtype=bf)
         ops.gemm(x4, wpr, bias=b1, aux=x, epilogue=L.EPI_BIAS_RESID, out=o1)
