@@ -91,7 +91,7 @@ typedef struct clipn_gemm_desc {
   const float* row_lse;          /* [M] */
   const float* col_lse;          /* [N] */
   float* part_max; float* part_sum; /* [2*ceil(N/BN) * M] each; BN from clipn_gemm_tile_n() */
-  float* pos;                    /* [M] label logit */
+  float* pos;                    /* [M] label logit (LSE: written); CLIP_DLOGITS: optional row centre (read) */
   float* scalar_acc;             /* [2] fp32 accumulators: d logit_scale (raw, pre-chain), d logit_bias */
   float logit_bias;              /* added to alpha*acc before exp (0 if none) */
   float gscale;                  /* gradient scale, e.g. 1/(2B) */
@@ -254,10 +254,13 @@ int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols, int32_t m
                        clipn_stream_t stream);
 /* dlogits (bf16 [m, ld]) for one direction, mean-centred and WITHOUT the one-hot term, see CLIPN_EPI_CLIP_DLOGITS;
  * col_lse is the OTHER direction's global LSE vector [n] (all ranks),
- * scalar_acc[0] += sum_{m,n} (P_row - onehot) * s / scale * gscale. */
+ * scalar_acc[0] += sum_{m,n} (P_row - onehot) * (s / scale - row_centre[m]) * gscale  — the d logit_scale sum.
+ * row_centre (optional fp32 [m]): any value close to rows[m] . cols[label_offset + m]; it cancels exactly
+ * (sum_n P_row = 1) and keeps the accumulated terms small while all features are still nearly parallel. */
 int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e, float scale,
                        const float* scale_dev, int32_t label_offset, const float* row_lse, const float* col_lse,
-                       float col_w, float gscale, void* dlogits, int64_t ld, float* scalar_acc, clipn_stream_t stream);
+                       float col_w, float gscale, void* dlogits, int64_t ld, float* scalar_acc, const float* row_centre,
+                       clipn_stream_t stream);
 /* d_rows (fp32 [m,E]) += alpha * dlogits[m,n] @ feats_cols[n,E]; split-K over n in `splits` chunks (TMA reduce-add)
  * so that the [m x E] output fills the machine.  The caller initialises d_rows: zeros, or for ClipLoss the fp32 part
  * (1+col_w) * gscale * alpha * (mean_n feats_cols[n] - feats_cols[label_offset + m]). */

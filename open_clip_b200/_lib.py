@@ -83,7 +83,7 @@ SIGNATURES = {
                                          _P, _P, _F, _P, _P, _P, _P, _P, _P, _I64, _P]),
     "clipn_clip_lse_workspace": (C.c_int64, [_I32, _I32]),
     "clipn_clip_lse_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I32, _P, _P, _P, _P]),
-    "clipn_clip_dlogits": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I32, _P, _P, _F, _F, _P, _I64, _P, _P]),
+    "clipn_clip_dlogits": (C.c_int, [_P, _P, _I32, _I32, _I32, _F, _P, _I32, _P, _P, _F, _F, _P, _I64, _P, _P, _P]),
     "clipn_clip_dfeat": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _F, _P, _P, _I32, _P]),
 }
 

@@ -541,12 +541,16 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
   uint64_t* pds_full = bars + 5;  // P and dS in shared memory (8 warps)
   uint64_t* out_full = bars + 6;  // dV, dK, dQ in TMEM
   uint64_t* acc_free = bars + 7;  // TMEM read by the epilogue (8 warps)
-  uint64_t* staged = bars + 8;    // dQ / dK / dV staged in the stage's tiles (8 warps) -> warps 2 and 3
-  uint64_t* sums_done = bars + 9; // warp 2 -> warp 3
-  uint64_t* stg_free = bars + 10; // G == 2: the staging tiles have been read by the stores and the sums (warp 3)
-  uint64_t* p_full = bars + 11;   // P in shared memory (8 warps): dV's MMAs start while dS is still being computed
-  uint64_t* dv_full = bars + 12;  // dV in TMEM
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  // `staged` and `sums_done` have TWO barriers each, alternating by item: with G == 1 nothing stops the epilogue warps
+  // (resp. warp 2) from completing item n+1's phase while a consumer is still waiting for item n's — on a single barrier
+  // the parity would then alias and the waiter hang (seen on 8 GPUs under NCCL traffic).  A consumer never lags by
+  // more than one item (item n+2 needs the input stage that item n's consumers release), so two barriers suffice.
+  uint64_t* staged = bars + 8;    // [2] dQ / dK / dV staged in the stage's tiles (8 warps) -> warps 2 and 3
+  uint64_t* sums_done = bars + 10; // [2] warp 2 -> warp 3
+  uint64_t* stg_free = bars + 12; // G == 2: the staging tiles have been read by the stores and the sums (warp 3)
+  uint64_t* p_full = bars + 13;   // P in shared memory (8 warps): dV's MMAs start while dS is still being computed
+  uint64_t* dv_full = bars + 14;  // dV in TMEM
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -568,8 +572,10 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
     mbar_init(pds_full, 8);
     mbar_init(out_full, 1);
     mbar_init(acc_free, 8);
-    mbar_init(staged, 8);
-    mbar_init(sums_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&staged[i], 8);
+      mbar_init(&sums_done[i], 1);
+    }
     mbar_init(stg_free, 1);
     mbar_init(p_full, 8);
     mbar_init(dv_full, 1);
@@ -680,7 +686,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
         flush();
         cur_h = h;
       }
-      mbar_wait(staged, n & 1);
+      mbar_wait(&staged[n & 1], (n >> 1) & 1);
       if (warp == 3 && lane == 0) {
         tma_store_3d(&tm.dqkv, st, h * 64, 0, b0);
         tma_store_3d(&tm.dqkv, st + AT_TILE, p.D + h * 64, 0, b0);
@@ -704,10 +710,10 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       }
       __syncwarp();
       if (warp == 2) {
-        if (lane == 0) mbar_arrive(sums_done);  // the dQ tile has been summed
+        if (lane == 0) mbar_arrive(&sums_done[n & 1]);  // the dQ tile has been summed
       } else if (lane == 0) {
         tma_store_wait_read<0>();       // the staged tiles have been read by the stores ...
-        mbar_wait(sums_done, n & 1);    // ... and by warp 2: they may be overwritten
+        mbar_wait(&sums_done[n & 1], (n >> 1) & 1);    // ... and by warp 2: they may be overwritten
         mbar_arrive(two ? stg_free : &in_empty[stage]);
       }
       __syncwarp();
@@ -842,7 +848,7 @@ attention_tc_bwd_kernel(const __grid_constant__ AttnBwdMaps tm, const __grid_con
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(acc_free);
-        mbar_arrive(staged);
+        mbar_arrive(&staged[n & 1]);
       }
       valid = nvalid_row;
       lse_raw = nlse_raw;

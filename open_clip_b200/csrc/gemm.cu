@@ -298,6 +298,11 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
       }
     }
     const float shift = (1.f + p.col_w) / static_cast<float>(p.n);
+    // d logit_scale = sum (P_row - onehot) * dot: with nearly parallel features (fresh model) every dot is ~1 and the sum
+    // is the small difference of two O(B) totals — accumulated naively (one fp32 atomic per warp and tile) it lost all
+    // but two digits at N = 32768.  Subtracting a per-row centre c ~ dot[row, label] (optional vector `pos`) from every
+    // dot changes the exact value by c * (sum_n P_row - 1) = 0 and leaves only small terms to accumulate.
+    const float centre = (p.pos != nullptr && row_ok) ? __ldg(p.pos + row) : 0.f;
     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
@@ -312,7 +317,7 @@ __device__ __forceinline__ void epi_compute(const GemmParams& p, int row, int co
       // The caller restores both parts in fp32: (1 + col_w) * gscale * alpha * (mean_n cols[n] - cols[label]).
       v[i] = p.gscale * (pr + pc - shift);
       if (has_label && col + i == label) pr -= 1.f;
-      a0 = fmaf(pr, dot, a0);
+      a0 = fmaf(pr, dot - centre, a0);
       a1 += pr;
     }
     if (row_ok) {

@@ -346,7 +346,7 @@ extern "C" int clipn_clip_lse_fwd(const void* feats_rows, const void* feats_cols
 extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols, int32_t m, int32_t n, int32_t e,
                                   float scale, const float* scale_dev, int32_t label_offset, const float* row_lse,
                                   const float* col_lse, float col_w, float gscale, void* dlogits, int64_t ld,
-                                  float* scalar_acc, clipn_stream_t stream) {
+                                  float* scalar_acc, const float* row_centre, clipn_stream_t stream) {
   CLIPN_REQUIRE(feats_rows && feats_cols && row_lse && dlogits, "clip_dlogits: null pointer");
   clipn_gemm_desc d;
   base_desc(d, feats_rows, feats_cols, m, n, e, scale, scale_dev);
@@ -354,6 +354,7 @@ extern "C" int clipn_clip_dlogits(const void* feats_rows, const void* feats_cols
   d.c = dlogits; d.ldc = ld;
   d.row_lse = row_lse; d.col_lse = col_lse; d.col_w = col_w; d.gscale = gscale;
   d.scalar_acc = scalar_acc;
+  d.pos = const_cast<float*>(row_centre);  // read-only here: per-row centre of the d logit_scale sum
   d.label_offset = label_offset;
   const void* bp[1] = {feats_cols};
   return gemm_launch(d, bp, 1, 0, false, static_cast<cudaStream_t>(stream));

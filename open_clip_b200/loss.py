@@ -117,10 +117,14 @@ class _ClipLossFn(torch.autograd.Function):
         coef = scale * ((1.0 + col_w) * gscale)  # [1] fp32 device scalar
         mean_t = ops.colsum(all_txt, torch.zeros(E, dtype=F32, device=img.device)) / N
         mean_i = ops.colsum(all_img, torch.zeros(E, dtype=F32, device=img.device)) / N
-        dl_i = ops.clip_dlogits(img, all_txt, scale, off, lse_i, all_lse_t if col_w else None, col_w, gscale, acc[0:2])
+        # per-row centre of the d logit_scale sum (clipn.h): the positive pair's cosine, the same for both directions
+        centre = (img.float() * txt.float()).sum(dim=-1).contiguous()
+        dl_i = ops.clip_dlogits(img, all_txt, scale, off, lse_i, all_lse_t if col_w else None, col_w, gscale, acc[0:2],
+                                row_centre=centre)
         d_img = ops.clip_dfeat(dl_i, all_txt, scale, n=N, init=(mean_t - txt.float()) * coef)
         del dl_i
-        dl_t = ops.clip_dlogits(txt, all_img, scale, off, lse_t, all_lse_i if col_w else None, col_w, gscale, acc[2:4])
+        dl_t = ops.clip_dlogits(txt, all_img, scale, off, lse_t, all_lse_i if col_w else None, col_w, gscale, acc[2:4],
+                                row_centre=centre)
         d_txt = ops.clip_dfeat(dl_t, all_img, scale, n=N, init=(mean_i - img.float()) * coef)
         del dl_t
         # d loss / d logit_scale = sum_{dir} sum (P_row - onehot) * <row, col> / (2B)   (own loss only)

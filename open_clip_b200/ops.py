@@ -376,7 +376,7 @@ def clip_lse_fwd(rows: torch.Tensor, cols: torch.Tensor, scale: torch.Tensor, la
     return lse, pos
 
 
-def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscale, scalar_acc):
+def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscale, scalar_acc, row_centre=None):
     _chk(rows, BF16, "dlogits.rows"); _chk(cols, BF16, "dlogits.cols")
     m, e = rows.shape
     n = cols.shape[0]
@@ -385,7 +385,7 @@ def clip_dlogits(rows, cols, scale, label_offset, row_lse, col_lse, col_w, gscal
     with _profiled((m, n, e, L.EPI_CLIP_DLOGITS, False, False)):
         _call(L.lib().clipn_clip_dlogits(rows.data_ptr(), cols.data_ptr(), m, n, e, 1.0, scale.data_ptr(), label_offset,
                                            row_lse.data_ptr(), _ptr(col_lse), col_w, gscale, out.data_ptr(), ld,
-                                           _ptr(scalar_acc), _stream()))
+                                           _ptr(scalar_acc), _ptr(row_centre), _stream()))
     return out
 
 

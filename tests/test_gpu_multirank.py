@@ -95,7 +95,11 @@ def _check_golden(rank, world):
             assert abs(float(loss) - want["loss"]) < 2e-2 + 1e-2 * abs(want["loss"]), (tag, float(loss), want["loss"])
             assert _rel(gi.grad, want["d_img"]) < 2e-2, (tag, "d_img", _rel(gi.grad, want["d_img"]))
             assert _rel(gt.grad, want["d_txt"]) < 2e-2, (tag, "d_txt", _rel(gt.grad, want["d_txt"]))
-            assert abs(float(gs.grad) - want["d_scale"]) < 3e-2 * abs(want["d_scale"]) + 1e-4, (tag, "d_scale")
+            # d logit_scale of one rank can be a near-cancellation of its positive and negative terms (SigLIP, W = 8:
+            # 0.002 on one rank against 0.09 on another): the error bar is set by the largest rank's value
+            ds_ref = max(abs(r["d_scale"]) for r in case["ranks"])
+            assert abs(float(gs.grad) - want["d_scale"]) < 3e-2 * ds_ref + 1e-4, (tag, "d_scale", float(gs.grad),
+                                                                                 want["d_scale"])
     os.environ["CLIPN_FORCE_NCCL_GATHER"] = "0"
 
 
