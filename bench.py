@@ -472,8 +472,10 @@ def main():
                          "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": traffic,
                          "traffic_source": traffic_src,
-                         "algorithmic_bytes": (2.0 * (top[0] * top[2] + top[1] * top[2]) +
-                                               2.0 * top[0] * top[1] * (2 if top[3] in (1, 9) else 1)) if top else None,
+                         # operands once + the epilogue's bytes per output element (bf16 tensors 2 B: BIAS_GELU(_GRAD) write
+                         # two, MUL_AUX / BIAS_RESID read one and write one, DGELU reads one and writes two; fp32 outputs 4 B)
+                         "algorithmic_bytes": (2.0 * (top[0] * top[2] + top[1] * top[2]) + top[0] * top[1] *
+                                               {1: 4, 2: 4, 3: 6, 4: 4, 5: 4, 9: 4, 10: 4}.get(top[3], 2)) if top else None,
                          "launches_timed": len(gemm_ms), "avg_launch_ms": avg_ms,
                          "flops_per_launch": flops_launch, "peak_source": peaks["source"] + ", sustained"},
             "roofline_gemm_family": {"bound": "tensor", "achieved": fam_flops / (fam_ms * 1e-3) / 1e12 if fam_ms else None,
