@@ -93,6 +93,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+_SMS: Optional[int] = None
+
+
+def _sm_count() -> int:
+    """SMs of the current device (clipn_device_info); 148 (B200) where no GPU is visible — the CPU test container."""
+    global _SMS
+    if _SMS is None:
+        _SMS = 148
+        if torch.cuda.is_available():
+            sms, major, minor = C.c_int(0), C.c_int(0), C.c_int(0)
+            if L.lib().clipn_device_info(C.byref(sms), C.byref(major), C.byref(minor)) == 0 and sms.value > 0:
+                _SMS = sms.value
+    return _SMS
+
+
 def wgrad_splits(m_out: int, n_out: int, k: int) -> int:
     """split-K factor for a weight-gradient GEMM: minimises rounds x (k-blocks per item + fixed cost per item), the
     fixed cost (accumulator drain + fp32 TMA reduce-add of the tile, pipeline fill) taken as 32 k-blocks.
@@ -101,7 +116,7 @@ def wgrad_splits(m_out: int, n_out: int, k: int) -> int:
     bn = L.lib().clipn_gemm_tile_n(n_out)
     tiles = ((m_out + 127) // 128) * ((n_out + bn - 1) // bn)
     kblocks = (k + 63) // 64
-    sms = 148
+    sms = _sm_count()
     best, best_cost = 1, float("inf")
     for s in range(1, 33):
         if s > 1 and kblocks // s < 16:   # keep >= 16 k-blocks (1024 rows) per work item

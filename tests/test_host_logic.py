@@ -230,3 +230,19 @@ def test_native_grad_sync_averages_per_block_gloo_world2():
     for rank, ok, order in res:
         assert ok, rank
         assert order == ["visual.transformer.resblocks.1", "visual.transformer.resblocks.0"]
+
+
+def test_wgrad_split_factor_cost_model():
+    """Split-K factor of the weight-gradient GEMMs (ops.wgrad_splits): rounds x (k-blocks per item + fixed cost).  Pins the
+    cases that were measured on B200: the [2304, 768] in_proj gradient must not get the 30 splits the
+    utilisation-only rule gave it (0.64 of peak; 8 splits: 0.89), its 2-split siblings stay at 2."""
+    from open_clip_b200 import ops
+    assert ops.wgrad_splits(2304, 768, 204800) == 8
+    assert ops.wgrad_splits(768, 3072, 204800) == 2
+    assert ops.wgrad_splits(3072, 768, 204800) == 2
+    assert ops.wgrad_splits(512, 2048, 315392) <= 12        # text MLP: was 23
+    for m, n, k in [(768, 768, 51200), (512, 512, 315392), (1024, 4096, 1181696), (592, 1024, 1181696), (512, 768, 4096),
+                    (768, 512, 64), (64, 64, 1 << 20)]:
+        s = ops.wgrad_splits(m, n, k)
+        assert 1 <= s <= 32
+        assert s == 1 or ((k + 63) // 64) // s >= 16          # at least 16 k-blocks (1024 rows) per work item
