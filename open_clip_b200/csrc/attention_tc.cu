@@ -473,14 +473,17 @@ attention_tc_fwd_kernel(const __grid_constant__ AttnMaps tm, const __grid_consta
 // Backward, sequences of at most 128 tokens (both CLIP ViT-B towers: 50 / 77; ViT-L text: 77) — one tile per item,
 // everything in one pass:
 //   S = Q K^T, dP = dO V^T               (TMEM, 2 x 128 columns)
-//   P = exp(S - lse), dS = P o (dP - D) * scale, D = rowsum(dO o O)      (8 warps: TMEM lane quarter x column half)
-//   dV = P^T dO, dK = dS^T Q, dQ = dS K  (TMEM, 3 x 64 columns)
+//   P = exp(S - lse), dS = P o (dP - D) * scale                          (8 warps: TMEM lane quarter x column half)
+//       D = rowsum(dO o O) = sum_key P dP  (O = P V; the whole key range of a row is in this tile), so the O tile is
+//       never loaded: the two column halves of a row exchange their fp32 partial sums through shared memory
+//   dV = P^T dO, dK = dS^T Q, dQ = dS K  (TMEM, 3 x 64 columns; dV on its own commit, drained while dK / dQ run)
 // P and dS are written once to shared memory in the SW128 layout that is at the same time the K-major operand
 // [q][key] (dQ = dS K) and the MN-major operand [key][q]^T (dV = P^T dO, dK = dS^T Q): no transposition anywhere.
 // Likewise every input tile [rows x 64] serves as K-major operand (contraction over head_dim) and MN-major operand
-// (contraction over rows) in its natural TMA layout.  Outputs leave through the input stage's own tiles (dQ over Q,
-// dK over K, dV over V) by three TMA stores; the in_proj bias gradient (column sums of dqkv) is accumulated per head
-// in shared memory and flushed with one atomicAdd per column when the CTA's contiguous item range changes head.
+// (contraction over rows) in its natural TMA layout.  Outputs leave by three TMA stores from staging tiles (their own
+// 48 KB when two sequences share a tile, else the input stage's Q / K / V tiles); the in_proj bias gradient (column sums
+// of the staged dQ / dV; the K third is identically zero) is summed by warps 2 / 3 in registers and flushed with one
+// atomicAdd per column when the CTA's contiguous item range changes head.
 // ===================================================================================================
 // Shared-memory plan (bytes): two input stages [Q, K, V, dO] = 128 K, then
 //   G == 2 (L <= 64, two sequences per tile): output staging [dQ, dK, dV] 48 K | P 24 K | dS 24 K — P and dS are block
