@@ -403,30 +403,10 @@ class NativeCLIP(nn.Module):
     def encode_text(self, text, normalize: bool = False):
         return self._run_tower("text", text, normalize)
 
-    def _forward_two_streams(self, image: torch.Tensor, text: torch.Tensor):
-        """Experimental (CLIPN_TOWER_STREAMS=1, not yet measured on hardware): the towers are independent until the
-        loss, so the text tower runs on a side stream and fills the tails of the vision tower's persistent kernels;
-        autograd replays each tower's backward on the stream its forward used."""
-        main = torch.cuda.current_stream(image.device)
-        side = getattr(self, "_side_stream", None)
-        if side is None or side.device != image.device:
-            side = self._side_stream = torch.cuda.Stream(device=image.device)
-        side.wait_stream(main)
-        text.record_stream(side)
-        with torch.cuda.stream(side):
-            text_features = self.encode_text(text, normalize=True)
-        image_features = self.encode_image(image, normalize=True)
-        main.wait_stream(side)
-        text_features.record_stream(main)
-        return image_features, text_features
-
     def forward(self, image: Optional[torch.Tensor] = None, text: Optional[torch.Tensor] = None):
         # model.py:528-548
-        if image is not None and text is not None and image.is_cuda and os.environ.get("CLIPN_TOWER_STREAMS") == "1":
-            image_features, text_features = self._forward_two_streams(image, text)
-        else:
-            image_features = self.encode_image(image, normalize=True) if image is not None else None
-            text_features = self.encode_text(text, normalize=True) if text is not None else None
+        image_features = self.encode_image(image, normalize=True) if image is not None else None
+        text_features = self.encode_text(text, normalize=True) if text is not None else None
         if self.output_dict:
             out = {"image_features": image_features, "text_features": text_features,
                    "logit_scale": self.logit_scale.exp()}
