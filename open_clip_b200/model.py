@@ -12,7 +12,6 @@ There is no CPU path: calling this on CPU tensors raises.
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict, List, Optional
 
 import torch
