@@ -246,3 +246,27 @@ def test_wgrad_split_factor_cost_model():
         s = ops.wgrad_splits(m, n, k)
         assert 1 <= s <= 32
         assert s == 1 or ((k + 63) // 64) // s >= 16          # at least 16 k-blocks (1024 rows) per work item
+
+
+def test_bench_parity_oracle_runs_in_fp64_and_why():
+    """bench.oracle_rank0 (the checker of the bench line's `parity` block): fp64 values, both losses; and the reason it is
+    fp64 — with nearly parallel features (a fresh model's: cos ~ 0.9998) the fp32 oracle's own d(logit_scale) is off by
+    ~0.1-1 % at a few thousand columns, the same size as the 2 % bar the kernels are held to, while the loss and
+    the feature gradients agree to 1e-4."""
+    import bench
+    torch.manual_seed(0)
+    W, B, E = 8, 256, 128
+    base = torch.nn.functional.normalize(torch.randn(1, E), dim=-1)
+    fi = [torch.nn.functional.normalize(base + 0.0012 * torch.randn(B, E), dim=-1).to(torch.bfloat16).float() for _ in range(W)]
+    ft = [torch.nn.functional.normalize(base + 0.0012 * torch.randn(B, E), dim=-1).to(torch.bfloat16).float() for _ in range(W)]
+    sc = torch.tensor(14.2857)
+    ref, d_img, d_txt, d_scale, dt = bench.oracle_rank0(fi, ft, sc, None, False)
+    assert dt == torch.float64 and ref.dtype == torch.float64 and d_img.dtype == torch.float64 and d_img.shape == (B, E)
+    from oracle import clip_oracle as O
+    r32 = O.clip_loss_rank_grads(fi, ft, sc, 0, True, True)
+    assert abs(float(r32[0]) - float(ref)) < 1e-4
+    assert float((r32[1].double() - d_img).norm() / d_img.norm()) < 1e-3
+    rel32 = abs(float(r32[3]) - float(d_scale)) / abs(float(d_scale))
+    assert rel32 < 0.2, rel32           # (typically 1e-4 .. 1e-2 here: cancellation in fp32, not a bug; 0.4-1 % at N = 32768)
+    out = bench.oracle_rank0(fi[:2], ft[:2], torch.tensor(10.0), torch.tensor(-10.0), True)
+    assert len(out) == 5 and out[4] == torch.float64 and out[1].shape == (B, E)
